@@ -1,0 +1,615 @@
+// C ABI of libmpn_b200.so (see include/mpn_b200.h).  Host-side orchestration only: argument checking, workspace
+// ownership, anchor tables, stream-ordered kernel launches.  There is no CPU implementation of any stage in this
+// library: without a CUDA device every entry point fails with MPN_ERR_CUDA.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "handle.cuh"
+
+using namespace mpn;
+
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+int fail(mpn_handle *h, int code, const char *fmt, ...)
+{
+    char *dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MPN_CUDA(h, call)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(h, MPN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int grid_size(int image, int stride) { return (int)std::ceil((float)image / (float)stride); }
+
+int count_anchors(const mpn_config &c, int H, int W)
+{
+    int a = 0;
+    for (int i = 0; i < c.num_levels; ++i) a += grid_size(H, c.strides[i]) * grid_size(W, c.strides[i]);
+    return a * c.num_multipliers * c.num_ratios;
+}
+
+// detector/anchor_generator.py:53-93,141-145: everything about the anchors that does not depend on (y, x)
+void build_anchor_table(const mpn_config &c, int H, int W, AnchorTable *t)
+{
+    memset(t, 0, sizeof(*t));
+    t->n_levels = c.num_levels;
+    t->n_loc = c.num_multipliers * c.num_ratios;
+    t->fH = (float)H;
+    t->fW = (float)W;
+    int off = 0;
+    for (int i = 0; i < c.num_levels; ++i) {
+        const float s = (float)c.strides[i];
+        t->gh[i] = grid_size(H, c.strides[i]);
+        t->gw[i] = grid_size(W, c.strides[i]);
+        t->off[i] = off;
+        off += t->gh[i] * t->gw[i] * t->n_loc;
+        t->stride[i] = s;
+        // offset = 0.5 * (image - (float(h) - 1.0) * stride); host code is built with -ffp-contract=off (no fma)
+        const float ty = ((float)t->gh[i] - 1.0f) * s;
+        const float tx = ((float)t->gw[i] - 1.0f) * s;
+        t->oy[i] = 0.5f * (t->fH - ty);
+        t->ox[i] = 0.5f * (t->fW - tx);
+        int k = 0;
+        for (int im = 0; im < c.num_multipliers; ++im)
+            for (int ir = 0; ir < c.num_ratios; ++ir, ++k) {
+                const float sc = (float)(c.multipliers[im] * c.scales[i]);   // python double product -> float32 constant
+                const float rs = sqrtf((float)c.ratios[ir]);
+                const float ah = sc / rs, aw = sc * rs;
+                t->half_h[i][k] = 0.5f * ah;
+                t->half_w[i][k] = 0.5f * aw;
+            }
+    }
+    t->off[c.num_levels] = off;
+    t->num_anchors = off;
+    for (int i = 0; i < 4; ++i) t->sf[i] = c.scale_factors[i];
+}
+
+// conservative logit pre-filter: every x below it has computed sigmoid(x) <= thr (sigmoid error < 3e-7 relative)
+float prefilter_logit(float thr)
+{
+    if (!(thr > 0.0f)) return -INFINITY;
+    if (thr >= 1.0f) return INFINITY;
+    const double t = (double)thr * (1.0 - 4e-6);
+    const double l = std::log(t / (1.0 - t));
+    return (float)(l - std::fabs(l) * 1e-6 - 1e-6);
+}
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+}
+
+int check_image_size(mpn_handle *h, int B, int H, int W)
+{
+    if (B < 1 || H < 1 || W < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "batch/height/width must be positive");
+    if (H % 128 != 0 || W % 128 != 0)   // inference/detector.py:45, detector/constants.py:4
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "image height and width must be divisible by 128 (got %dx%d)", H, W);
+    if (B > h->cfg.max_batch || H > h->cfg.max_height || W > h->cfg.max_width)
+        return fail(h, MPN_ERR_CAPACITY, "call %dx%dx%d exceeds handle capacity %dx%dx%d", B, H, W, h->cfg.max_batch,
+                    h->cfg.max_height, h->cfg.max_width);
+    return MPN_OK;
+}
+
+int check_params(mpn_handle *h, const mpn_params *p)
+{
+    if (!p) return fail(h, MPN_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (p->max_detections < 1 || p->max_detections > h->cfg.max_detections)
+        return fail(h, MPN_ERR_CAPACITY, "max_detections %d outside [1, %d]", p->max_detections, h->cfg.max_detections);
+    if (!(p->iou_threshold >= 0.0f && p->iou_threshold <= 1.0f))
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "iou_threshold must be in [0, 1]");   // as the TF op requires
+    if (p->prn_mode != MPN_PRN_FP32 && p->prn_mode != MPN_PRN_BF16)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "unknown prn_mode %d", p->prn_mode);
+    return MPN_OK;
+}
+
+void count(mpn_handle *h, int n, bool first)
+{
+    if (first) h->last_launches = 0;
+    h->last_launches += n;
+    h->total_launches += n;
+}
+
+int launched(mpn_handle *h, int n, bool first, const char *what)
+{
+    if (n < 0) return fail(h, MPN_ERR_CUDA, "%s: %s", what, cudaGetErrorString((cudaError_t)(-n)));
+    count(h, n, first);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(h, MPN_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    return MPN_OK;
+}
+
+int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores, int *num_boxes,
+              int *sel_anchor, int *n_candidates, int *offsets_out, cudaStream_t s, bool first)
+{
+    int rc = check_image_size(h, in->batch, in->height, in->width);
+    if (rc) return rc;
+    rc = check_params(h, p);
+    if (rc) return rc;
+    const bool flat = in->class_logits != nullptr && in->encoded_boxes != nullptr;
+    const bool levels = in->level_class != nullptr && in->level_boxes != nullptr;
+    if (!flat && !levels)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "need class_logits+encoded_boxes or level_class+level_boxes");
+    if (!boxes || !scores || !num_boxes) return fail(h, MPN_ERR_INVALID_ARGUMENT, "boxes/scores/num_boxes is NULL");
+    AnchorTable t;
+    build_anchor_table(h->cfg, in->height, in->width, &t);
+    DetectArgs a;
+    memset(&a, 0, sizeof(a));
+    if (flat) {
+        if (reinterpret_cast<uintptr_t>(in->encoded_boxes) % 16 != 0)
+            return fail(h, MPN_ERR_INVALID_ARGUMENT, "encoded_boxes must be 16-byte aligned");
+        a.cls = in->class_logits;
+        a.enc = in->encoded_boxes;
+    } else {
+        for (int i = 0; i < t.n_levels; ++i) {
+            if (!in->level_class[i] || !in->level_boxes[i])
+                return fail(h, MPN_ERR_INVALID_ARGUMENT, "level %d pointer is NULL", i);
+            a.lv.cls[i] = in->level_class[i];
+            a.lv.box[i] = in->level_boxes[i];
+        }
+    }
+    a.B = in->batch;
+    a.thr = p->score_threshold;
+    a.iou_thr = p->iou_threshold;
+    a.pre_thr = prefilter_logit(p->score_threshold);
+    a.max_det = p->max_detections;
+    a.cand_keys = h->cand_keys;
+    a.key_cap = h->key_cap;
+    a.cand_count = h->cand_count;
+    a.done_counter = h->done_counter;
+    a.boxes = boxes;
+    a.scores = scores;
+    a.num_boxes = num_boxes;
+    a.sel_anchor = sel_anchor;
+    a.n_candidates = n_candidates;
+    a.person_box = h->person_box;
+    a.person_img = h->person_img;
+    a.person_offsets = h->person_offsets;
+    a.person_offsets_out = offsets_out;
+    return launched(h, launch_detect(t, a, s), first, "detect");
+}
+
+int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const int *n_dev, int n_host, int n_max,
+           int mode, float *logits, cudaStream_t s, bool first)
+{
+    if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
+    PrnWeights w;
+    w.D = h->D; w.hidden = h->cfg.prn_hidden;
+    w.W1 = h->W1; w.b1 = h->b1; w.W2 = h->W2; w.b2 = h->b2; w.W1t = h->W1t; w.W2t = h->W2t;
+    if (mode == MPN_PRN_FP32) {
+        if (!(h->cfg.prn_modes & 1)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the fp32 PRN");
+        return launched(h, launch_prn_fp32(w, h->prn_ws, x_f32, n_dev, n_host, n_max, logits, s), first, "prn fp32");
+    }
+    if (!(h->cfg.prn_modes & 2)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
+    return launched(h, launch_prn_bf16(w, h->prn_ws, x_f32, x_bf16, n_dev, n_host, n_max, logits, h->tmaps, s), first,
+                    "prn bf16");
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpn_version(void) { return 100; }
+
+const char *mpn_last_error(const mpn_handle *h) { return h ? h->err : g_create_error; }
+
+int mpn_default_config(mpn_config *c)
+{
+    if (!c) return MPN_ERR_INVALID_ARGUMENT;
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(mpn_config);
+    c->device = 0;
+    c->max_batch = 1;
+    c->max_height = 640;
+    c->max_width = 640;
+    c->max_detections = 25;                           // create_pb.py:35
+    c->num_levels = 5;                                // detector/retinanet.py:38-43
+    const int strides[5] = {8, 16, 32, 64, 128};
+    const double scales[5] = {32, 64, 128, 256, 512};
+    for (int i = 0; i < 5; ++i) { c->strides[i] = strides[i]; c->scales[i] = scales[i]; }
+    c->num_multipliers = 2; c->multipliers[0] = 1.0; c->multipliers[1] = 1.4142;
+    c->num_ratios = 3; c->ratios[0] = 1.0; c->ratios[1] = 2.0; c->ratios[2] = 0.5;
+    c->scale_factors[0] = 10.0f; c->scale_factors[1] = 10.0f; c->scale_factors[2] = 5.0f; c->scale_factors[3] = 5.0f;
+    c->crop_height = 56; c->crop_width = 36;          // create_pb.py:19
+    c->num_keypoints = 17; c->downsample = 4;         // detector/constants.py:10,13
+    c->prn_hidden = 1024;                             // detector/prn.py:20
+    c->prn_modes = 3;
+    return MPN_OK;
+}
+
+int mpn_create(const mpn_config *cfg, mpn_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(mpn_config))
+        return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "mpn_config size mismatch (%d vs %d)", cfg->struct_size,
+                    (int)sizeof(mpn_config));
+    if (cfg->num_levels < 1 || cfg->num_levels > kMaxLevels || cfg->num_multipliers < 1 || cfg->num_ratios < 1 ||
+        cfg->num_multipliers * cfg->num_ratios > kMaxShapes)
+        return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "bad anchor specification");
+    if (cfg->num_keypoints != 17 || cfg->downsample != 4)
+        return fail(nullptr, MPN_ERR_UNSUPPORTED, "kernels are built for 17 keypoints (+1 mask channel), downsample 4");
+    if (cfg->crop_height < 1 || cfg->crop_width < 1 || cfg->crop_height * cfg->crop_width > 2048)
+        return fail(nullptr, MPN_ERR_UNSUPPORTED, "crop size must have at most 2048 positions");
+    if (cfg->max_batch < 1 || cfg->max_detections < 1 || cfg->max_detections > kMaxDetCap)
+        return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "max_batch >= 1 and 1 <= max_detections <= %d required", kMaxDetCap);
+    if (cfg->max_height % 128 || cfg->max_width % 128 || cfg->max_height < 128 || cfg->max_width < 128)
+        return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "max_height/max_width must be positive multiples of 128");
+    if (cfg->prn_hidden % 64 != 0) return fail(nullptr, MPN_ERR_UNSUPPORTED, "prn_hidden must be a multiple of 64");
+    for (int i = 0; i < cfg->num_levels; ++i)
+        if (cfg->strides[i] < 1) return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "stride %d is not positive", i);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MPN_ERR_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MPN_ERR_INVALID_ARGUMENT, "device %d of %d", cfg->device, ndev);
+    MPN_CUDA(nullptr, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    MPN_CUDA(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, MPN_ERR_UNSUPPORTED, "kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+
+    mpn_handle *h = new (std::nothrow) mpn_handle;
+    if (!h) return fail(nullptr, MPN_ERR_CUDA, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->D = cfg->crop_height * cfg->crop_width * cfg->num_keypoints;
+    if (h->D % 32 != 0) { delete h; return fail(nullptr, MPN_ERR_UNSUPPORTED, "PRN width %d must be a multiple of 32", h->D); }
+    h->max_anchors = count_anchors(*cfg, cfg->max_height, cfg->max_width);
+    h->key_cap = 1;
+    while (h->key_cap < h->max_anchors) h->key_cap <<= 1;
+    h->max_hm_pix = (cfg->max_height / 4) * (cfg->max_width / 4);
+    h->max_persons = cfg->max_batch * cfg->max_detections;
+    const size_t B = cfg->max_batch, NP = h->max_persons, D = h->D, Hd = cfg->prn_hidden;
+    const size_t NPpad = (NP + 127) / 128 * 128;
+
+#define MPN_ALLOC(ptr, n)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e2 = dalloc(&(ptr), (n));                                                               \
+        if (e2 != cudaSuccess) {                                                                            \
+            fail(nullptr, MPN_ERR_CUDA, "cudaMalloc(%s, %zu elements) failed: %s", #ptr, (size_t)(n), cudaGetErrorString(e2)); \
+            mpn_destroy(h);                                                                                 \
+            return MPN_ERR_CUDA;                                                                            \
+        }                                                                                                   \
+    } while (0)
+
+    MPN_ALLOC(h->cand_keys, B * h->key_cap);
+    MPN_ALLOC(h->cand_count, B);
+    MPN_ALLOC(h->done_counter, 1);
+    MPN_ALLOC(h->person_box, NP * 4);
+    MPN_ALLOC(h->person_img, NP);
+    MPN_ALLOC(h->person_offsets, B + 1);
+    MPN_ALLOC(h->kh_ws, B * h->max_hm_pix * 17);
+    MPN_ALLOC(h->minmax_ws, B * 17 * 2);
+    MPN_ALLOC(h->crops_f32, NPpad * D);
+    MPN_ALLOC(h->logits, NPpad * D);
+    MPN_ALLOC(h->b1, Hd);
+    MPN_ALLOC(h->b2, D);
+    if (cfg->prn_modes & 1) {
+        MPN_ALLOC(h->W1, D * Hd);
+        MPN_ALLOC(h->W2, Hd * D);
+        h->prn_ws.partial_floats = (NP > 2400 ? NP : 2400) * Hd;
+        MPN_ALLOC(h->prn_ws.partial, h->prn_ws.partial_floats);
+        MPN_ALLOC(h->prn_ws.y1, NPpad * Hd);
+    }
+    if (cfg->prn_modes & 2) {
+        MPN_ALLOC(h->W1t, D * Hd);
+        MPN_ALLOC(h->W2t, Hd * D);
+        MPN_ALLOC(h->crops_bf16, NPpad * D);
+        MPN_ALLOC(h->prn_ws.y1_bf16, NPpad * Hd);
+        if (!h->prn_ws.partial) {
+            h->prn_ws.partial_floats = (NPpad > 2432 ? NPpad : 2432) * Hd;
+            MPN_ALLOC(h->prn_ws.partial, h->prn_ws.partial_floats);
+        }
+        cudaMemset(h->crops_bf16, 0, NPpad * D * sizeof(__nv_bfloat16));
+        cudaMemset(h->prn_ws.y1_bf16, 0, NPpad * Hd * sizeof(__nv_bfloat16));
+    }
+    h->prn_ws.n_max = (int)NPpad;
+    cudaMemset(h->done_counter, 0, sizeof(unsigned int));
+    cudaMemset(h->person_offsets, 0, (B + 1) * sizeof(int));
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->own_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        fail(nullptr, MPN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+        mpn_destroy(h);
+        return MPN_ERR_CUDA;
+    }
+    if (cfg->prn_modes & 2) {
+        int rc = prn_bf16_prepare(h);
+        if (rc != MPN_OK) {
+            snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+            mpn_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return MPN_OK;
+}
+
+void mpn_destroy(mpn_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    prn_bf16_release(h);
+    void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
+                    h->kh_ws, h->minmax_ws, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
+                    h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16, h->st_cls, h->st_enc, h->st_hml,
+                    h->st_boxes, h->st_scores, h->st_seg, h->st_kscores, h->st_kpos, h->st_num, h->st_offsets};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->own_event) cudaEventDestroy(h->own_event);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int mpn_num_anchors(const mpn_handle *h, int32_t height, int32_t width)
+{
+    if (!h || height < 1 || width < 1) return MPN_ERR_INVALID_ARGUMENT;
+    return count_anchors(h->cfg, height, width);
+}
+
+int mpn_set_prn_weights(mpn_handle *h, const float *W1, const float *b1, const float *W2, const float *b2)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!W1 || !b1 || !W2 || !b2) return fail(h, MPN_ERR_INVALID_ARGUMENT, "weight pointer is NULL");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t D = h->D, Hd = h->cfg.prn_hidden;
+    cudaStream_t s = h->own_stream;
+    // fp32 master copies; when only the bf16 PRN is configured they are staged through the logits workspace
+    float *dW1 = h->W1, *dW2 = h->W2;
+    const bool temp = !(h->cfg.prn_modes & 1);
+    if (temp) {
+        MPN_CUDA(h, dalloc(&dW1, D * Hd));
+        cudaError_t e = dalloc(&dW2, Hd * D);
+        if (e != cudaSuccess) { cudaFree(dW1); return fail(h, MPN_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    }
+    MPN_CUDA(h, cudaMemcpyAsync(dW1, W1, D * Hd * sizeof(float), cudaMemcpyHostToDevice, s));
+    MPN_CUDA(h, cudaMemcpyAsync(dW2, W2, Hd * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    MPN_CUDA(h, cudaMemcpyAsync(h->b1, b1, Hd * sizeof(float), cudaMemcpyHostToDevice, s));
+    MPN_CUDA(h, cudaMemcpyAsync(h->b2, b2, D * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (h->cfg.prn_modes & 2) {
+        // bf16 B operands, K-major: W1t [hidden, D], W2t [D, hidden]
+        launch_transpose_to_bf16(dW1, (int)D, (int)Hd, h->W1t, s);
+        launch_transpose_to_bf16(dW2, (int)Hd, (int)D, h->W2t, s);
+    }
+    MPN_CUDA(h, cudaStreamSynchronize(s));
+    if (temp) { cudaFree(dW1); cudaFree(dW2); }
+    MPN_CUDA(h, cudaGetLastError());
+    h->have_weights = true;
+    return MPN_OK;
+}
+
+int mpn_anchors(mpn_handle *h, int32_t height, int32_t width, float *anchors_out, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!anchors_out || height < 1 || width < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad arguments");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    AnchorTable t;
+    build_anchor_table(h->cfg, height, width, &t);
+    return launched(h, launch_anchors(t, anchors_out, (cudaStream_t)stream), true, "anchors");
+}
+
+int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores,
+               int32_t *num_boxes, int32_t *sel_anchor, int32_t *n_candidates, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!in) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs is NULL");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return do_detect(h, in, p, boxes, scores, num_boxes, sel_anchor, n_candidates, nullptr, (cudaStream_t)stream, true);
+}
+
+int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
+                 float *keypoint_heatmaps, float *segmentation_masks, float *minmax, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!heatmap_logits || !keypoint_heatmaps) return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap pointer is NULL");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(h, MPN_ERR_CAPACITY, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (hm_height < 1 || hm_width < 1 || (hm_height * hm_width) % 64 != 0)
+        return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 64 (it is for images divisible by 128)");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_heatmaps(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
+                                       h->minmax_ws, minmax, (cudaStream_t)stream), true, "heatmaps");
+}
+
+int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
+             int32_t hm_width, const float *boxes, const int32_t *box_ind, int32_t n, float *crops, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!keypoint_heatmaps || !boxes || !box_ind || !crops) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
+    if (n < 0 || batch < 1 || hm_height < 1 || hm_width < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad sizes");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_crop(keypoint_heatmaps, minmax, hm_height, hm_width, boxes, box_ind, nullptr, n, n,
+                                   h->cfg.crop_height, h->cfg.crop_width, crops, nullptr, (cudaStream_t)stream), true, "crop");
+}
+
+int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, float *logits, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!crops || !logits) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
+    if (n < 0 || n > h->prn_ws.n_max) return fail(h, MPN_ERR_CAPACITY, "n %d outside [0, %d]", n, h->prn_ws.n_max);
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) { h->last_launches = 0; return MPN_OK; }
+    bool first = true;
+    if (prn_mode == MPN_PRN_BF16) {
+        if (!h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
+        int rc = launched(h, launch_f32_to_bf16(crops, h->crops_bf16, nullptr, n, h->D, n, s), true, "bf16 convert");
+        if (rc) return rc;
+        first = false;
+    }
+    return do_prn(h, crops, h->crops_bf16, nullptr, n, n, prn_mode, logits, s, first);
+}
+
+int mpn_keypoint_decode(mpn_handle *h, const float *logits, int32_t n, float *scores, float *positions,
+                        int32_t *argmax, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!logits || !scores || !positions) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
+    if (n < 0) return fail(h, MPN_ERR_INVALID_ARGUMENT, "n is negative");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_keypoint_decode(logits, nullptr, n, n, h->cfg.crop_height, h->cfg.crop_width, scores,
+                                              positions, argmax, (cudaStream_t)stream), true, "keypoint decode");
+}
+
+int mpn_get_keypoints(mpn_handle *h, const float *heatmaps, int32_t hh, int32_t ww, const double box[4],
+                      double threshold, int32_t *out, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!heatmaps || !box || !out || hh < 1 || ww < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad arguments");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_get_keypoints(heatmaps, hh, ww, box[0], box[1], box[2], box[3], threshold, out,
+                                            (cudaStream_t)stream), true, "get_keypoints");
+}
+
+int mpn_test_exp(mpn_handle *h, const float *x, float *y, int64_t n, void *stream)
+{
+    if (!h || !x || !y || n < 0) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_test_math(x, y, n, 0, (cudaStream_t)stream), true, "test exp");
+}
+
+int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *stream)
+{
+    if (!h || !x || !y || n < 0) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_test_math(x, y, n, 1, (cudaStream_t)stream), true, "test sigmoid");
+}
+
+int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!in || !p || !out) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs/params/outputs is NULL");
+    if (!in->heatmap_logits) return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits is NULL");
+    if (!out->keypoint_scores || !out->keypoint_positions)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "keypoint_scores/keypoint_positions is NULL");
+    if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
+    int rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, s, true);
+    if (rc) return rc;
+    // 2. heatmap sigmoid / split / min-max                   (create_pb.py:73-76, 90, 92)
+    const int hh = in->height / h->cfg.downsample, ww = in->width / h->cfg.downsample;
+    float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
+    rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
+                                     nullptr, s), false, "heatmaps");
+    if (rc) return rc;
+    // 3. normalise + crop_and_resize                         (create_pb.py:93-94, 106-109)
+    const int n_max = in->batch * p->max_detections;
+    const int *n_dev = h->person_offsets + in->batch;
+    const bool bf16 = p->prn_mode == MPN_PRN_BF16;
+    if (bf16 && !h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
+    rc = launched(h, launch_crop(kh, h->minmax_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
+                                 h->cfg.crop_height, h->cfg.crop_width, h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
+                  false, "crop");
+    if (rc) return rc;
+    // 4. PRN                                                 (detector/prn.py:5-25)
+    rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, h->logits, s, false);
+    if (rc) return rc;
+    // 5. softmax / argmax                                    (create_pb.py:115-142)
+    return launched(h, launch_keypoint_decode(h->logits, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
+                                              out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
+                    "keypoint decode");
+}
+
+static int ensure_staging(mpn_handle *h)
+{
+    if (h->staging_ready) return MPN_OK;
+    const size_t B = h->cfg.max_batch, A = h->max_anchors, P = h->max_hm_pix, NP = h->max_persons;
+    MPN_CUDA(h, dalloc(&h->st_cls, B * A));
+    MPN_CUDA(h, dalloc(&h->st_enc, B * A * 4));
+    MPN_CUDA(h, dalloc(&h->st_hml, B * P * 18));
+    MPN_CUDA(h, dalloc(&h->st_boxes, NP * 4));
+    MPN_CUDA(h, dalloc(&h->st_scores, NP));
+    MPN_CUDA(h, dalloc(&h->st_seg, B * P));
+    MPN_CUDA(h, dalloc(&h->st_kscores, NP * 17));
+    MPN_CUDA(h, dalloc(&h->st_kpos, NP * 34));
+    MPN_CUDA(h, dalloc(&h->st_num, B));
+    MPN_CUDA(h, dalloc(&h->st_offsets, B + 1));
+    h->staging_ready = true;
+    return MPN_OK;
+}
+
+int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!in || !p || !out) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs/params/outputs is NULL");
+    if (!in->class_logits || !in->encoded_boxes || !in->heatmap_logits)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "mpn_run_host takes the concatenated layout: class_logits, encoded_boxes, heatmap_logits");
+    if (!out->boxes || !out->scores || !out->num_boxes || !out->keypoint_scores || !out->keypoint_positions)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "output pointer is NULL");
+    int rc = check_image_size(h, in->batch, in->height, in->width);
+    if (rc) return rc;
+    rc = check_params(h, p);
+    if (rc) return rc;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    rc = ensure_staging(h);
+    if (rc) return rc;
+    cudaStream_t s = h->own_stream;
+    const size_t B = in->batch, A = count_anchors(h->cfg, in->height, in->width);
+    const size_t P = (size_t)(in->height / 4) * (in->width / 4), NP = B * p->max_detections;
+    // feed (inference/detector.py:47)
+    MPN_CUDA(h, cudaMemcpyAsync(h->st_cls, in->class_logits, B * A * 4, cudaMemcpyHostToDevice, s));
+    MPN_CUDA(h, cudaMemcpyAsync(h->st_enc, in->encoded_boxes, B * A * 16, cudaMemcpyHostToDevice, s));
+    MPN_CUDA(h, cudaMemcpyAsync(h->st_hml, in->heatmap_logits, B * P * 72, cudaMemcpyHostToDevice, s));
+    mpn_inputs din = *in;
+    din.class_logits = h->st_cls; din.encoded_boxes = h->st_enc; din.heatmap_logits = h->st_hml;
+    din.level_class = nullptr; din.level_boxes = nullptr;
+    mpn_outputs dout;
+    dout.boxes = h->st_boxes; dout.scores = h->st_scores; dout.num_boxes = h->st_num;
+    dout.keypoint_heatmaps = h->kh_ws; dout.segmentation_masks = out->segmentation_masks ? h->st_seg : nullptr;
+    dout.keypoint_scores = h->st_kscores; dout.keypoint_positions = h->st_kpos; dout.person_offsets = h->st_offsets;
+    rc = mpn_run(h, &din, p, &dout, s);
+    if (rc) return rc;
+    // fetch (inference/detector.py:48)
+    MPN_CUDA(h, cudaMemcpyAsync(out->boxes, h->st_boxes, NP * 16, cudaMemcpyDeviceToHost, s));
+    MPN_CUDA(h, cudaMemcpyAsync(out->scores, h->st_scores, NP * 4, cudaMemcpyDeviceToHost, s));
+    MPN_CUDA(h, cudaMemcpyAsync(out->num_boxes, h->st_num, B * 4, cudaMemcpyDeviceToHost, s));
+    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_scores, h->st_kscores, NP * 17 * 4, cudaMemcpyDeviceToHost, s));
+    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_positions, h->st_kpos, NP * 34 * 4, cudaMemcpyDeviceToHost, s));
+    if (out->person_offsets)
+        MPN_CUDA(h, cudaMemcpyAsync(out->person_offsets, h->st_offsets, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    if (out->keypoint_heatmaps)
+        MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_heatmaps, h->kh_ws, B * P * 68, cudaMemcpyDeviceToHost, s));
+    if (out->segmentation_masks)
+        MPN_CUDA(h, cudaMemcpyAsync(out->segmentation_masks, h->st_seg, B * P * 4, cudaMemcpyDeviceToHost, s));
+    return MPN_OK;
+}
+
+int mpn_synchronize(mpn_handle *h)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    MPN_CUDA(h, cudaStreamSynchronize(h->own_stream));
+    return MPN_OK;
+}
+
+int mpn_launch_count(const mpn_handle *h, int64_t *last_call, int64_t *total)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (last_call) *last_call = h->last_launches;
+    if (total) *total = h->total_launches;
+    return MPN_OK;
+}
+
+}  // extern "C"

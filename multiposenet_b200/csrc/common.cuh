@@ -1,0 +1,99 @@
+// Internal declarations shared by the kernels and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/mpn_b200.h"
+
+namespace mpn {
+
+constexpr int kMaxLevels = MPN_MAX_LEVELS;
+constexpr int kMaxShapes = MPN_MAX_ANCHOR_SHAPES;
+constexpr int kSortSmemCap = 8192;      // candidates per image sorted in shared memory; above: global scratch
+constexpr int kMaxDetCap = 1024;        // kept boxes staged in shared memory
+
+// Everything the kernels need to rebuild anchor `a` from its index (detector/anchor_generator.py:53-116)
+// without an anchor tensor in HBM.  Passed by value (~1.3 KB of kernel parameters).
+struct AnchorTable {
+    int n_levels, n_loc, num_anchors;
+    int gh[kMaxLevels], gw[kMaxLevels];
+    int off[kMaxLevels + 1];              // first anchor index of each level
+    float stride[kMaxLevels], oy[kMaxLevels], ox[kMaxLevels];
+    float half_h[kMaxLevels][kMaxShapes]; // 0.5 * scale / sqrt(ratio)
+    float half_w[kMaxLevels][kMaxShapes]; // 0.5 * scale * sqrt(ratio)
+    float fH, fW;
+    float sf[4];                          // SCALE_FACTORS (detector/constants.py:19)
+};
+
+// Per-level NCHW head outputs (detector/box_predictor.py:53-90 fused away); NULL => concatenated layout.
+struct LevelPtrs {
+    const float *cls[kMaxLevels];
+    const float *box[kMaxLevels];
+};
+
+struct DetectArgs {
+    const float *cls;        // [B, A] or NULL
+    const float *enc;        // [B, A, 4] or NULL
+    LevelPtrs lv;            // used when cls == NULL
+    int B;
+    float thr, iou_thr, pre_thr;
+    int max_det;
+    // workspace
+    unsigned long long *cand_keys;   // [B, key_cap]
+    int key_cap;                     // power of two >= A
+    int *cand_count;                 // [B]
+    unsigned int *done_counter;      // [1]
+    // outputs
+    float *boxes;            // [B, max_det, 4]
+    float *scores;           // [B, max_det]
+    int *num_boxes;          // [B]
+    int *sel_anchor;         // [B, max_det] or NULL
+    int *n_candidates;       // [B] or NULL
+    // person list (create_pb.py:96-103)
+    float *person_box;       // [B*max_det, 4]
+    int *person_img;         // [B*max_det]
+    int *person_offsets;     // [B+1]
+    int *person_offsets_out; // user copy [B+1] or NULL
+};
+
+// ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
+int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
+int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s);
+
+int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
+                    float *minmax_out, cudaStream_t s);
+int launch_crop(const float *kh, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
+                const int *n_dev, int n_host, int n_max, int crop_h, int crop_w, float *crops_f32,
+                __nv_bfloat16 *crops_bf16, cudaStream_t s);
+int launch_get_keypoints(const float *hm, int hh, int ww, double ymin, double xmin, double ymax, double xmax,
+                         double threshold, int *out, cudaStream_t s);
+
+int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
+                           float *scores, float *positions, int *argmax, cudaStream_t s);
+
+struct PrnWeights {
+    int D, hidden;
+    const float *W1, *b1, *W2, *b2;                 // fp32, [in,out] row-major
+    const __nv_bfloat16 *W1t, *W2t;                 // bf16, transposed to [out,in] (K-major B operands)
+};
+struct PrnWorkspace {
+    float *partial;          // split-K partial sums of fc1
+    size_t partial_floats;
+    float *y1;               // [n_max, hidden] fp32
+    __nv_bfloat16 *y1_bf16;  // [n_max_pad, hidden]
+    int n_max;
+};
+int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x, const int *n_dev, int n_host,
+                    int n_max, float *logits, cudaStream_t s);
+int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_f32, const __nv_bfloat16 *x_bf16,
+                    const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, cudaStream_t s);
+int launch_fc1_reduce(const float *partial, int splits, size_t split_stride, const float *bias, int hidden,
+                      const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, cudaStream_t s);
+int launch_f32_to_bf16(const float *x, __nv_bfloat16 *y, const int *n_rows_dev, int n_rows_host, int row_len,
+                       int n_rows_max, cudaStream_t s);
+int launch_transpose_to_bf16(const float *w, int rows, int cols, __nv_bfloat16 *wt, cudaStream_t s);
+
+int launch_test_math(const float *x, float *y, int64_t n, int which, cudaStream_t s);
+
+}  // namespace mpn

@@ -1,0 +1,320 @@
+// Anchors, score threshold, candidate compaction, sort and greedy NMS.
+//
+// Replaces (reference, TensorFlow graph ops):
+//   detector/anchor_generator.py:40-116      anchors -- never materialised here, rebuilt from the anchor index
+//   detector/box_predictor.py:53-90          reshape_and_concatenate -- fused into the loads (NCHW variant)
+//   detector/retinanet.py:73                 scores = sigmoid(class_predictions)
+//   detector/utils/nms.py:27-53              threshold, boolean_mask, decode, clip, NonMaxSuppressionV3, gather, pad
+//   detector/utils/box_utils.py:112-139      decode
+//   create_pb.py:96-103                      flat person list (boxes, box_ind) in image order
+//
+// Kernel 1 (candidates_*): HBM-bound scan of the class logits.  A cheap conservative logit test rejects the
+//   ~99.7 % background anchors; survivors get the exact sigmoid and a strict `> thr` test and are appended to a
+//   per-image candidate list as 64-bit keys (score bits << 32 | ~anchor), so that a descending key order is
+//   (score desc, anchor index asc) -- the matched tie-break of the oracle.
+// Kernel 2 (sort_nms): one CTA per image.  Bitonic sort of the keys (shared memory up to 8192 candidates, the
+//   image's global scratch above that -- exact for any candidate count), then greedy NMS in chunks of 1024
+//   candidates: every thread decodes its candidate's box (4 gathered codes + anchor from the index), tests it
+//   against the boxes kept so far, and the chunk is resolved with ballots, two barriers per kept box.  The last
+//   CTA to finish builds the flat person list.
+#include "common.cuh"
+#include "mpn_math.cuh"
+
+namespace mpn {
+
+namespace {
+
+constexpr int kNmsThreads = 1024;
+
+struct Anchor { float ymin, xmin, ymax, xmax; };
+
+__device__ __forceinline__ int level_of(const AnchorTable &t, int a)
+{
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < t.n_levels && a >= t.off[i]) l = i;
+    return l;
+}
+
+// detector/anchor_generator.py:92-93,141-165,110-114 in the reference's operation order
+__device__ __forceinline__ Anchor anchor_from_index(const AnchorTable &t, int a, int *level_out, int *loc_out,
+                                                    int *k_out)
+{
+    const int l = level_of(t, a);
+    const int r = a - t.off[l];
+    const int k = r % t.n_loc, loc = r / t.n_loc;
+    const int y = loc / t.gw[l], x = loc - y * t.gw[l];
+    const float cy = fadd(fmul((float)y, t.stride[l]), t.oy[l]);
+    const float cx = fadd(fmul((float)x, t.stride[l]), t.ox[l]);
+    const float hh = t.half_h[l][k], hw = t.half_w[l][k];
+    Anchor an;
+    an.ymin = fdiv(fsub(cy, hh), t.fH);
+    an.xmin = fdiv(fsub(cx, hw), t.fW);
+    an.ymax = fdiv(fadd(cy, hh), t.fH);
+    an.xmax = fdiv(fadd(cx, hw), t.fW);
+    if (level_out) { *level_out = l; *loc_out = loc; *k_out = k; }
+    return an;
+}
+
+// detector/utils/box_utils.py:73-76,124-139 + clip of detector/utils/nms.py:36
+__device__ __forceinline__ float4 decode_box(const Anchor an, const float4 code, const float *sf)
+{
+    const float ha = fsub(an.ymax, an.ymin), wa = fsub(an.xmax, an.xmin);
+    const float cya = fadd(an.ymin, fmul(0.5f, ha)), cxa = fadd(an.xmin, fmul(0.5f, wa));
+    const float ty = fdiv(code.x, sf[0]), tx = fdiv(code.y, sf[1]);
+    const float th = fdiv(code.z, sf[2]), tw = fdiv(code.w, sf[3]);
+    const float h = fmul(exact_expf(th), ha), w = fmul(exact_expf(tw), wa);
+    const float cy = fadd(fmul(ty, ha), cya), cx = fadd(fmul(tx, wa), cxa);
+    const float hh = fmul(0.5f, h), hw = fmul(0.5f, w);
+    return make_float4(clip01(fsub(cy, hh)), clip01(fsub(cx, hw)), clip01(fadd(cy, hh)), clip01(fadd(cx, hw)));
+}
+
+__device__ __forceinline__ void push_candidate(const DetectArgs &a, int img, int anchor, float logit)
+{
+    const float s = exact_sigmoidf(logit);
+    if (s > a.thr) {   // == thr passes nms.py:30 but can never be selected by the NMS op (strict >)
+        const int slot = atomicAdd(a.cand_count + img, 1);
+        const unsigned long long key =
+            ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)anchor);
+        a.cand_keys[(size_t)img * a.key_cap + slot] = key;
+    }
+}
+
+__global__ void anchors_kernel(const AnchorTable t, float4 *out)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= t.num_anchors) return;
+    const Anchor an = anchor_from_index(t, a, nullptr, nullptr, nullptr);
+    out[a] = make_float4(an.ymin, an.xmin, an.ymax, an.xmax);
+}
+
+__global__ void detect_reset_kernel(int *cand_count, unsigned int *done_counter, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) cand_count[i] = 0;
+    if (i == 0) *done_counter = 0u;
+}
+
+// Concatenated [B, A] logits, 4 per thread as one 16-byte load over the flat array.
+__global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a, const int A, const long long total,
+                                                              const int vec_ok)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e0 = t * 4;
+    if (e0 >= total) return;
+    float v[4];
+    int n = 4;
+    if (vec_ok && e0 + 4 <= total) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(a.cls) + t);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+        n = (int)min(4LL, total - e0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (j < n) ? __ldg(a.cls + e0 + j) : -__int_as_float(0x7f800000);
+    }
+    if (!((v[0] > a.pre_thr) | (v[1] > a.pre_thr) | (v[2] > a.pre_thr) | (v[3] > a.pre_thr))) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < n && v[j] > a.pre_thr) {
+            const long long e = e0 + j;
+            const int img = (int)(e / A);
+            push_candidate(a, img, (int)(e - (long long)img * A), v[j]);
+        }
+    }
+}
+
+// Per-level NCHW logits [B, n_loc, gh, gw]: threads walk memory order, anchor index = off + (y*gw+x)*n_loc + k.
+__global__ void __launch_bounds__(256) candidates_nchw_kernel(const AnchorTable t, const DetectArgs a)
+{
+    const int img = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // position inside the image's concatenated levels
+    if (e >= t.num_anchors) return;
+    const int l = level_of(t, e);
+    const int r = e - t.off[l];
+    const int plane = t.gh[l] * t.gw[l];
+    const float v = __ldg(a.lv.cls[l] + (size_t)img * plane * t.n_loc + r);
+    if (v > a.pre_thr) {
+        const int k = r / plane, loc = r - k * plane;
+        push_candidate(a, img, t.off[l] + loc * t.n_loc + k, v);
+    }
+}
+
+__device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectArgs &a, int img, int anchor, int l,
+                                            int loc, int k)
+{
+    if (a.enc) return __ldg(reinterpret_cast<const float4 *>(a.enc) + (size_t)img * t.num_anchors + anchor);
+    const int plane = t.gh[l] * t.gw[l];
+    const float *p = a.lv.box[l] + ((size_t)img * t.n_loc * 4 + (size_t)k * 4) * plane + loc;   // channel k*4+coord
+    return make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane), __ldg(p + 3 * plane));
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);            // [kSortSmemCap]
+    float4 *kept_box = reinterpret_cast<float4 *>(smem_raw + sizeof(unsigned long long) * kSortSmemCap);  // [max_det]
+    __shared__ int s_first[32];
+    __shared__ int s_is_last;
+
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = min(a.cand_count[img], a.key_cap);
+    unsigned long long *gkeys = a.cand_keys + (size_t)img * a.key_cap;
+    unsigned long long *keys;
+    int npad = 1;
+    while (npad < C) npad <<= 1;
+    if (C <= kSortSmemCap) {
+        keys = skeys;
+        for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = (i < C) ? gkeys[i] : 0ULL;
+    } else {
+        keys = gkeys;
+        for (int i = C + tid; i < npad; i += kNmsThreads) gkeys[i] = 0ULL;
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < (npad >> 1); p += kNmsThreads) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long x = keys[i], y = keys[ixj];
+                const bool desc = (i & k) == 0;
+                if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
+            }
+            __syncthreads();
+        }
+    }
+
+    float *boxes_out = a.boxes + (size_t)img * a.max_det * 4;
+    float *scores_out = a.scores + (size_t)img * a.max_det;
+    int kept = 0;
+    for (int base = 0; base < C && kept < a.max_det; base += kNmsThreads) {
+        const int i = base + tid;
+        bool alive = i < C;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        int anchor = -1;
+        if (alive) {
+            const unsigned long long key = keys[i];
+            score = __uint_as_float((unsigned)(key >> 32));
+            anchor = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            int l, loc, k;
+            const Anchor an = anchor_from_index(t, anchor, &l, &loc, &k);
+            box = decode_box(an, load_code(t, a, img, anchor, l, loc, k), t.sf);
+            for (int j = kept - 1; j >= 0; --j)
+                if (nms_iou(box, kept_box[j]) > a.iou_thr) { alive = false; break; }
+        }
+        // resolve the chunk in score order: the first live candidate is kept, then suppresses the rest
+        while (kept < a.max_det) {
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) s_first[warp] = m ? (warp * 32 + __ffs(m) - 1) : 0x7fffffff;
+            __syncthreads();
+            int first = s_first[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            if (first == 0x7fffffff) break;     // uniform: every thread reads the same s_first
+            if (tid == first) {
+                kept_box[kept] = box;
+                reinterpret_cast<float4 *>(boxes_out)[kept] = box;
+                scores_out[kept] = score;
+                if (a.sel_anchor) a.sel_anchor[(size_t)img * a.max_det + kept] = anchor;
+                alive = false;
+            }
+            __syncthreads();
+            const float4 kb = kept_box[kept];
+            ++kept;
+            if (alive && nms_iou(box, kb) > a.iou_thr) alive = false;
+        }
+        __syncthreads();   // s_first / kept_box stable before the next chunk
+    }
+    // zero padding (detector/utils/nms.py:47-52)
+    for (int k = kept + tid; k < a.max_det; k += kNmsThreads) {
+        reinterpret_cast<float4 *>(boxes_out)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        scores_out[k] = 0.f;
+        if (a.sel_anchor) a.sel_anchor[(size_t)img * a.max_det + k] = -1;
+    }
+    if (tid == 0) {
+        a.num_boxes[img] = kept;
+        if (a.n_candidates) a.n_candidates[img] = C;
+    }
+    // ---- last CTA: flat person list in image order (create_pb.py:96-103) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(a.done_counter, 1u);
+        s_is_last = (done == (unsigned)a.B - 1u);
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    if (warp == 0) {
+        int running = 0;
+        for (int b0 = 0; b0 < a.B; b0 += 32) {
+            const int b = b0 + lane;
+            const int n = (b < a.B) ? __ldcg(a.num_boxes + b) : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < a.B) {
+                a.person_offsets[b] = running + incl - n;
+                if (a.person_offsets_out) a.person_offsets_out[b] = running + incl - n;
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            a.person_offsets[a.B] = running;
+            if (a.person_offsets_out) a.person_offsets_out[a.B] = running;
+            *a.done_counter = 0u;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < a.B * a.max_det; idx += kNmsThreads) {
+        const int b = idx / a.max_det, k = idx - b * a.max_det;
+        if (k < __ldcg(a.num_boxes + b)) {
+            const int row = a.person_offsets[b] + k;
+            reinterpret_cast<float4 *>(a.person_box)[row] = __ldcg(reinterpret_cast<const float4 *>(a.boxes) + idx);
+            a.person_img[row] = b;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
+{
+    anchors_kernel<<<(t.num_anchors + 255) / 256, 256, 0, s>>>(t, reinterpret_cast<float4 *>(out));
+    return 1;
+}
+
+int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
+{
+    static bool attr_set = false;
+    const size_t smem = sizeof(unsigned long long) * kSortSmemCap + sizeof(float4) * (size_t)a.max_det;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(unsigned long long) * kSortSmemCap + sizeof(float4) * kMaxDetCap));
+        if (e != cudaSuccess) return -(int)e;
+        attr_set = true;
+    }
+    int launches = 0;
+    detect_reset_kernel<<<(a.B + 255) / 256, 256, 0, s>>>(a.cand_count, a.done_counter, a.B);
+    ++launches;
+    if (a.cls) {
+        const long long total = (long long)a.B * t.num_anchors;
+        const long long threads = (total + 3) / 4;
+        const int vec_ok = (reinterpret_cast<uintptr_t>(a.cls) % 16 == 0) ? 1 : 0;
+        candidates_flat_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, t.num_anchors, total, vec_ok);
+    } else {
+        dim3 grid((t.num_anchors + 255) / 256, a.B);
+        candidates_nchw_kernel<<<grid, 256, 0, s>>>(t, a);
+    }
+    ++launches;
+    sort_nms_kernel<<<a.B, kNmsThreads, smem, s>>>(t, a);
+    ++launches;
+    return launches;
+}
+
+}  // namespace mpn

@@ -1,0 +1,40 @@
+// The handle behind the C ABI (opaque to callers).
+#pragma once
+#include "common.cuh"
+
+struct mpn_handle {
+    mpn_config cfg;
+    int D;                  // crop_h * crop_w * num_keypoints
+    int max_anchors, key_cap, max_hm_pix, max_persons;
+    char err[512];
+    cudaStream_t own_stream;
+    cudaEvent_t own_event;
+    // detect workspace
+    unsigned long long *cand_keys;
+    int *cand_count;
+    unsigned int *done_counter;
+    float *person_box;
+    int *person_img;
+    int *person_offsets;
+    // heatmap workspace
+    float *kh_ws;
+    float *minmax_ws;
+    // PRN workspace / weights
+    float *crops_f32, *logits;
+    __nv_bfloat16 *crops_bf16;
+    float *W1, *b1, *W2, *b2;
+    __nv_bfloat16 *W1t, *W2t;
+    mpn::PrnWorkspace prn_ws;
+    void *tmaps;            // opaque: prn_tcgen05.cu
+    bool have_weights;
+    // device staging for mpn_run_host
+    float *st_cls, *st_enc, *st_hml, *st_boxes, *st_scores, *st_seg, *st_kscores, *st_kpos;
+    int *st_num, *st_offsets;
+    bool staging_ready;
+    int64_t last_launches, total_launches;
+};
+
+namespace mpn {
+int prn_bf16_prepare(mpn_handle *h);   // prn_tcgen05.cu: TMA tensor maps for the bf16 GEMMs
+void prn_bf16_release(mpn_handle *h);
+}
