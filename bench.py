@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the post-backbone path (decode + NMS + crop + PRN + keypoint decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2] [--prn-mode bf16]
+
+A "step" is one pass of the hot path over one batch of synthetic post-backbone tensors of BASELINE.json's
+configs[1] (640x640, batch 8, 9 anchors / location, score thr 0.3, NMS IoU 0.5, <= 25 boxes per image) PER GPU.
+With N > 1 (torchrun, one process per GPU) every rank runs its own batch: images shard across ranks with no
+collective on the data path, so scaling is "weak" and `value` is the aggregate over ranks
+divided by the slowest rank's device time.
+
+Legs (all in one run, one JSON line on rank 0):
+  value      inputs already resident in HBM, outputs left in HBM; K steps back to back on one stream, CUDA events.
+             Inputs rotate over a ring of distinct batches whose total size exceeds the 126 MB L2 (no flush needed).
+  e2e        the same steps through the reference-facing call with HOST buffers: pinned host -> device copies of
+             the step's inputs, the path, and device -> host copies of all seven outputs (heatmaps included, as
+             Detector.__call__ fetches them) inside the timed region; wall clock bracketed by synchronisation.
+  roofline   per-kernel CUDA-event times of K more steps (mpn_set_profiling); the dominant kernel's algorithmic
+             bytes / its average duration against MEASURED_PEAKS.json.
+  cpu_baseline   the CPU oracle port (oracle/, BLAS for the two dense layers) on the host cores, bounded sample.
+--impl reference runs only the CPU leg as the reference arm (TensorFlow 1.15 cannot be installed: DESIGN.md).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "images/sec post-backbone (decode+NMS+PRN)"
+UNIT = "images/s"
+D = 56 * 36 * 17
+HIDDEN = 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--prn-mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        self.marks = []
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self, t0, t1):
+        self.marks.append((t0, t1))
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if any(a - 0.05 <= t <= b + 0.15 for a, b in self.marks)] or \
+               [r for (_, r) in self.rows]
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- workload
+def make_ring(wl, n_sets, rank):
+    from multiposenet_b200 import synthetic
+    return [synthetic.make_inputs(wl, replicate=100 * rank + r) for r in range(n_sets)]
+
+
+def set_bytes(inp):
+    return sum(int(inp[k].nbytes) for k in ("class_logits", "encoded_boxes", "heatmap_logits"))
+
+
+def algorithmic_bytes(kernel, wl, B, n_persons, n_cand, mode):
+    """Compulsory HBM traffic of one launch ('Kernels and their rooflines')."""
+    A, pix = wl.num_anchors, (wl.height // 4) * (wl.width // 4)
+    wbytes = 2 if mode == "bf16" else 4
+    table = {
+        "candidates_flat": 4 * A * B + 8 * n_cand,
+        "sort_nms": 8 * n_cand + 16 * n_cand + B * wl.max_detections * 20,
+        "heatmap": 72 * pix * B + 72 * pix * B,
+        "crop": n_persons * D * (4 + (2 if mode == "bf16" else 0)),
+        "prn_bf16_fc1": D * HIDDEN * 2 + n_persons * D * 2,
+        "prn_bf16_fc2": D * HIDDEN * 2 + n_persons * (HIDDEN * 2 + D * 4 + D * 4),
+        "prn_fp32_fc1": D * HIDDEN * 4 + n_persons * D * 4,
+        "prn_fp32_fc2": D * HIDDEN * 4 + n_persons * (HIDDEN * 4 + D * 4 + D * 4),
+        "keypoint_decode": n_persons * D * 4,
+    }
+    del wbytes
+    return table.get(kernel)
+
+
+# ------------------------------------------------------------------------------------------------- CPU leg
+def cpu_port_runner(wl, weights):
+    """One batch through the oracle port (CPU restatement of the reference path); BLAS (torch CPU, all host
+    threads) for the two dense layers, OpenMP C for the rest."""
+    import torch
+
+    import oracle
+    W1, b1, W2, b2 = [torch.from_numpy(np.ascontiguousarray(a)) for a in weights]
+
+    def prn_fn(x):
+        xt = torch.from_numpy(x)
+        y1 = torch.relu(torch.addmm(b1, xt, W1))
+        return (xt + torch.relu(torch.addmm(b2, y1, W2))).numpy()
+
+    def run(inp):
+        return oracle.full_path(inp["class_logits"], inp["encoded_boxes"], inp["heatmap_logits"], wl.height, wl.width,
+                                *weights, thr=wl.score_threshold, iou_thr=wl.iou_threshold, max_det=wl.max_detections,
+                                multipliers=wl.multipliers, ratios=wl.ratios, prn_fn=prn_fn)
+    return run
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_leg(wl, weights, ring, seconds, max_steps=None, warmup=2):
+    run = cpu_port_runner(wl, weights)
+    for i in range(warmup):
+        run(ring[i % len(ring)])
+    n, t0 = 0, time.perf_counter()
+    times = []
+    while True:
+        t = time.perf_counter()
+        run(ring[n % len(ring)])
+        times.append(time.perf_counter() - t)
+        n += 1
+        if (max_steps is not None and n >= max_steps) or (max_steps is None and time.perf_counter() - t0 >= seconds):
+            break
+    total = sum(times)
+    B = ring[0]["class_logits"].shape[0]
+    return {"value": B * n / total, "unit": UNIT, "cores": host_cores(), "kind": "port",
+            "sample": f"{n} batches of {B} images ({wl.name}), {total:.1f} s of CPU work; oracle C port + torch CPU "
+                      f"BLAS for the PRN (TensorFlow 1.15 not installable: restatement, not TF)",
+            "ms_per_step": 1e3 * total / n, "steps": n}
+
+
+def reference_arm(args, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.15 (the reference's only
+    backend) cannot be installed here (no network, no cp312 wheel), so this times the oracle port."""
+    if rank != 0:
+        return
+    from multiposenet_b200 import synthetic
+    weights = synthetic.make_prn_weights()
+    ring = make_ring(wl, 2, 0)
+    steps = max(1, min(args.steps, 400))
+    res = run_cpu_leg(wl, weights, ring, seconds=0, max_steps=steps, warmup=max(1, min(args.warmup, 5)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(wl, args, ring_sets=2),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(wl, args, ring_sets):
+    return {"workload": f"BASELINE configs[1]: {wl.name}", "image": [wl.height, wl.width], "batch_per_gpu": wl.batch,
+            "anchors_per_location": wl.n_loc, "anchors_per_image": wl.num_anchors,
+            "score_threshold": wl.score_threshold, "iou_threshold": wl.iou_threshold,
+            "max_detections": wl.max_detections, "prn": args.prn_mode, "parallelism": f"dp{args.gpus} (image-sharded, no collective)",
+            "l2": f"inputs rotate over {ring_sets} distinct batches (> 126 MB L2 in total), no flush"}
+
+
+# ------------------------------------------------------------------------------------------------- GPU legs
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from multiposenet_b200 import synthetic
+    wl = synthetic.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from multiposenet_b200 import Detector, DetectorConfig
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    weights = synthetic.make_prn_weights()
+    det = Detector(weights, DetectorConfig(
+        max_batch=wl.batch, max_height=wl.height, max_width=wl.width, max_boxes=wl.max_detections,
+        score_threshold=wl.score_threshold, iou_threshold=wl.iou_threshold, scale_multipliers=wl.multipliers,
+        aspect_ratios=wl.ratios, prn_mode=args.prn_mode, prn_modes_allocated=(args.prn_mode,), device=local_rank))
+
+    probe = synthetic.make_inputs(wl, replicate=100 * rank)
+    n_sets = max(2, -(-int(1.3 * L2_BYTES) // set_bytes(probe)))
+    ring = [probe] + [synthetic.make_inputs(wl, replicate=100 * rank + r) for r in range(1, n_sets)]
+    names = ("encoded_boxes", "class_logits", "heatmap_logits")
+    dev_ring = [{k: torch.from_numpy(s[k]).to(dev) for k in names} for s in ring]
+    pin_ring = [{k: torch.from_numpy(s[k]).pin_memory() for k in names} for s in ring]
+    B = wl.batch
+
+    def dev_step(i):
+        s = dev_ring[i % n_sets]
+        return det.run_device(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], (wl.height, wl.width))
+
+    def host_step(i):
+        s = pin_ring[i % n_sets]
+        out = det.run_host_async(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], (wl.height, wl.width),
+                                 return_heatmaps=True)
+        det.synchronize()
+        return out
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- leg 1: device-resident ------------------------------------------------------------------------------
+    for i in range(Wm):
+        out = dev_step(i)
+    barrier()
+    _, launches0 = det.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(K):
+        out = dev_step(Wm + i)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    if sampler:
+        sampler.mark(t0, t1)
+    _, launches1 = det.launch_count()
+    dev_ms = e0.elapsed_time(e1)
+    persons = int(out["person_offsets"][-1].item())
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+
+    # ---- leg 2: end to end through host buffers --------------------------------------------------------------
+    for i in range(Wm):
+        host_step(i)
+    barrier()
+    t0 = time.time()
+    w0 = time.perf_counter()
+    for i in range(K):
+        hout = host_step(Wm + i)
+        _ = int(hout["num_boxes"][0])          # the step's result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    t1 = time.time()
+    if sampler:
+        sampler.mark(t0, t1)
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = set_bytes(ring[0])
+    d2h = sum(int(v.numel() * v.element_size()) for v in hout.values())
+
+    clocks = sampler.stop() if sampler else None
+
+    # ---- leg 3: per-kernel times (profiling events; not part of `value`) ---------------------------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        det.set_profiling(True)
+        acc, order = {}, []
+        n_cand = 0
+        for i in range(min(K, 50)):
+            dev_step(i)
+            for name, ms in det.profile():
+                if name not in acc:
+                    acc[name] = []
+                    order.append(name)
+                acc[name].append(ms)
+        det.set_profiling(False)
+        s = dev_ring[0]
+        dstat = det.detect(s["encoded_boxes"], s["class_logits"], (wl.height, wl.width))
+        n_cand = int(dstat["n_candidates"].sum().item())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        kernels = {}
+        step_ms = sum(statistics.mean(v) for v in acc.values())
+        for name in order:
+            ms = statistics.mean(acc[name])
+            ab = algorithmic_bytes(name, wl, B, persons, n_cand, args.prn_mode)
+            kernels[name] = {"ms": round(ms, 5), "share": round(ms / step_ms, 4),
+                             "alg_bytes": ab, "gbs": None if not ab else round(ab / ms / 1e6, 1)}
+        top = max(order, key=lambda n: statistics.mean(acc[n]))
+        ab = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
+        ach = ab / statistics.mean(acc[top]) / 1e6
+        roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": which,
+                    "alg_bytes_per_launch": ab, "avg_launch_ms": round(statistics.mean(acc[top]), 5),
+                    "persons_per_batch": persons, "candidates_per_batch": n_cand}
+
+    # ---- leg 4: CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = run_cpu_leg(wl, weights, ring, seconds=args.cpu_seconds)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    det.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    images = B * K * world
+    line = {
+        "metric": METRIC, "value": images / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (decode/NMS/crop/softmax) + " + ("bf16 tcgen05, f32 accumulate (PRN)" if args.prn_mode == "bf16" else "f32 (PRN)"),
+        "data": "synthetic", "config": config_dict(wl, args, n_sets),
+        "e2e": {"value": images / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / K},
+        "gpu_launches": int(launches1 - launches0),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define MPN_API __attribute__((visibility("default")))
+#else
+#define MPN_API
+#endif
+
 #define MPN_MAX_LEVELS 8
 #define MPN_MAX_ANCHOR_SHAPES 16
 
@@ -119,67 +125,74 @@ typedef struct mpn_outputs {
 
 typedef struct mpn_handle mpn_handle;
 
-int mpn_version(void);
-const char *mpn_last_error(const mpn_handle *h);      /* h may be NULL: last error of a failed mpn_create */
-int mpn_default_config(mpn_config *cfg);              /* the reference's constants; capacity 1 x 640 x 640 x 25 */
+MPN_API int mpn_version(void);
+MPN_API const char *mpn_last_error(const mpn_handle *h);      /* h may be NULL: last error of a failed mpn_create */
+MPN_API int mpn_default_config(mpn_config *cfg);              /* the reference's constants; capacity 1 x 640 x 640 x 25 */
 
-int mpn_create(const mpn_config *cfg, mpn_handle **out);
-void mpn_destroy(mpn_handle *h);
-int mpn_num_anchors(const mpn_handle *h, int32_t height, int32_t width);   /* >0, or negative status */
+MPN_API int mpn_create(const mpn_config *cfg, mpn_handle **out);
+MPN_API void mpn_destroy(mpn_handle *h);
+MPN_API int mpn_num_anchors(const mpn_handle *h, int32_t height, int32_t width);   /* >0, or negative status */
 
 /* PRN variables PRN/fc1/{weights,biases}, PRN/fc2/{weights,biases} (detector/prn.py:13,20,22; restored at
  * create_pb.py:182-185).  Host pointers, fp32, [in,out] row-major as slim stores them:
  * W1 [D, hidden], b1 [hidden], W2 [hidden, D], b2 [D], D = crop_height*crop_width*num_keypoints.    */
-int mpn_set_prn_weights(mpn_handle *h, const float *W1, const float *b1, const float *W2, const float *b2);
+MPN_API int mpn_set_prn_weights(mpn_handle *h, const float *W1, const float *b1, const float *W2, const float *b2);
 
 /* The whole path, device pointers in and out: create_pb.py:73-147 (+ detector/retinanet.py:56-81,
  * detector/utils/nms.py:6-61, detector/prn.py:5-25).  Asynchronous on `stream`.                      */
-int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream);
+MPN_API int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream);
 
 /* Same with HOST pointers for inputs and outputs: what Detector.__call__'s feed_dict / fetch does at
  * inference/detector.py:47-48.  Copies in, runs, copies out on the handle's own stream; returns after
  * enqueueing when the buffers are pinned.  mpn_synchronize waits for completion.                     */
-int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out);
-int mpn_synchronize(mpn_handle *h);
+MPN_API int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out);
+MPN_API int mpn_synchronize(mpn_handle *h);
 
 /* ---- single stages (device pointers), used by the parity tests and by the PRN-only sweep ---- */
 
 /* anchors [A,4]: detector/anchor_generator.py:40-116 (the run path never materialises them) */
-int mpn_anchors(mpn_handle *h, int32_t height, int32_t width, float *anchors_out, void *stream);
+MPN_API int mpn_anchors(mpn_handle *h, int32_t height, int32_t width, float *anchors_out, void *stream);
 
 /* detector/retinanet.py:73 + detector/utils/nms.py:6-61.  sel_anchor [B,max_det] i32 (optional): anchor index of
  * every kept box (-1 padded); n_candidates [B] i32 (optional): anchors with score > threshold.      */
-int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores,
+MPN_API int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores,
                int32_t *num_boxes, int32_t *sel_anchor, int32_t *n_candidates, void *stream);
 
 /* create_pb.py:73-76 and the min / max of :90,92.  minmax [B, K, 2] f32 (optional) = (min, max) per image, channel */
-int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
+MPN_API int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
                  float *keypoint_heatmaps, float *segmentation_masks, float *minmax, void *stream);
 
 /* create_pb.py:90-94 + tf.image.crop_and_resize create_pb.py:106-109.  boxes [N,4], box_ind [N] i32,
  * minmax [B,K,2] or NULL (no normalisation) -> crops [N, crop_h, crop_w, K] f32                        */
-int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
+MPN_API int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
              int32_t hm_width, const float *boxes, const int32_t *box_ind, int32_t n, float *crops, void *stream);
 
 /* detector/prn.py:5-25: crops [N, D] f32 -> logits [N, D] f32 */
-int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, float *logits, void *stream);
+MPN_API int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, float *logits, void *stream);
 
 /* create_pb.py:115-142: logits [N, crop_h*crop_w, K] -> scores [N,K], positions [N,K,2], argmax [N,K] i32 (optional) */
-int mpn_keypoint_decode(mpn_handle *h, const float *logits, int32_t n, float *scores, float *positions,
+MPN_API int mpn_keypoint_decode(mpn_handle *h, const float *logits, int32_t n, float *scores, float *positions,
                         int32_t *argmax, void *stream);
 
 /* inference/utils.py:29-52 get_keypoints: heatmaps [hh, ww, K] f32 (device), box (ymin,xmin,ymax,xmax) and threshold as
  * Python floats -> out [K,3] i32 (device) rows (x, y, visible)                                             */
-int mpn_get_keypoints(mpn_handle *h, const float *heatmaps, int32_t hh, int32_t ww, const double box[4],
+MPN_API int mpn_get_keypoints(mpn_handle *h, const float *heatmaps, int32_t hh, int32_t ww, const double box[4],
                       double threshold, int32_t *out, void *stream);
 
 /* Element-wise device exp / sigmoid of the path (bit-level test hooks): y[i] = f(x[i]) */
-int mpn_test_exp(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
-int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
+MPN_API int mpn_test_exp(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
+MPN_API int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
+
+/* Per-kernel device times of the most recent mpn_run (CUDA events recorded on the run's stream between the kernels;
+ * used by bench.py for the roofline figures -- leave it off in production, every event costs a little launch time).
+ * mpn_get_profile waits for the run to finish; names[i] are static strings, ms[i] the time from the launch of kernel i
+ * to the launch of kernel i+1 (or the end of the run).                                                     */
+MPN_API int mpn_set_profiling(mpn_handle *h, int32_t enable);
+MPN_API int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names, float *ms, int32_t *count);
 
 /* Counters of the most recent run (valid after the stream has been synchronised): number of kernels launched by the
  * last mpn_run / stage call, and the sum over calls since creation.                                       */
-int mpn_launch_count(const mpn_handle *h, int64_t *last_call, int64_t *total);
+MPN_API int mpn_launch_count(const mpn_handle *h, int64_t *last_call, int64_t *total);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,10 @@
 
 using namespace mpn;
 
+namespace mpn {
+thread_local Profiler *g_prof = nullptr;
+}
+
 
 namespace {
 
@@ -135,6 +139,20 @@ int launched(mpn_handle *h, int n, bool first, const char *what)
     if (e != cudaSuccess) return fail(h, MPN_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
     return MPN_OK;
 }
+
+// Arms the per-kernel profiler for the duration of one run call and records the closing event.
+struct ProfScope {
+    mpn_handle *h;
+    cudaStream_t s;
+    ProfScope(mpn_handle *h_, cudaStream_t s_) : h(h_), s(s_)
+    {
+        if (h->prof.on) { h->prof.n = 0; g_prof = &h->prof; }
+    }
+    ~ProfScope()
+    {
+        if (h->prof.on) { cudaEventRecord(h->prof.ev[h->prof.n], s); g_prof = nullptr; }
+    }
+};
 
 int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores, int *num_boxes,
               int *sel_anchor, int *n_candidates, int *offsets_out, cudaStream_t s, bool first)
@@ -273,7 +291,11 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->D = cfg->crop_height * cfg->crop_width * cfg->num_keypoints;
-    if (h->D % 32 != 0) { delete h; return fail(nullptr, MPN_ERR_UNSUPPORTED, "PRN width %d must be a multiple of 32", h->D); }
+    if (h->D % 32 != 0) {
+        const int d = h->D;
+        delete h;
+        return fail(nullptr, MPN_ERR_UNSUPPORTED, "PRN width %d must be a multiple of 32", d);
+    }
     h->max_anchors = count_anchors(*cfg, cfg->max_height, cfg->max_width);
     h->key_cap = 1;
     while (h->key_cap < h->max_anchors) h->key_cap <<= 1;
@@ -357,6 +379,8 @@ void mpn_destroy(mpn_handle *h)
                     h->st_boxes, h->st_scores, h->st_seg, h->st_kscores, h->st_kpos, h->st_num, h->st_offsets};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (h->prof_events_ready)
+        for (int i = 0; i <= kMaxMarks; ++i) cudaEventDestroy(h->prof.ev[i]);
     if (h->own_event) cudaEventDestroy(h->own_event);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -505,6 +529,7 @@ int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_
     if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof_scope(h, s);
     // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
     int rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, s, true);
     if (rc) return rc;
@@ -601,6 +626,35 @@ int mpn_synchronize(mpn_handle *h)
     if (!h) return MPN_ERR_INVALID_ARGUMENT;
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     MPN_CUDA(h, cudaStreamSynchronize(h->own_stream));
+    return MPN_OK;
+}
+
+int mpn_set_profiling(mpn_handle *h, int32_t enable)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (enable && !h->prof_events_ready) {
+        for (int i = 0; i <= kMaxMarks; ++i) MPN_CUDA(h, cudaEventCreate(&h->prof.ev[i]));
+        h->prof_events_ready = true;
+    }
+    h->prof.on = enable != 0;
+    h->prof.n = 0;
+    return MPN_OK;
+}
+
+int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names, float *ms, int32_t *count)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!names || !ms || !count || capacity < 0) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->prof.on) return fail(h, MPN_ERR_INVALID_ARGUMENT, "profiling is off (mpn_set_profiling)");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int n = h->prof.n < capacity ? h->prof.n : capacity;
+    if (h->prof.n > 0) MPN_CUDA(h, cudaEventSynchronize(h->prof.ev[h->prof.n]));
+    for (int i = 0; i < n; ++i) {
+        names[i] = h->prof.name[i];
+        MPN_CUDA(h, cudaEventElapsedTime(&ms[i], h->prof.ev[i], h->prof.ev[i + 1]));
+    }
+    *count = n;
     return MPN_OK;
 }
 

@@ -57,6 +57,24 @@ struct DetectArgs {
     int *person_offsets_out; // user copy [B+1] or NULL
 };
 
+// Optional per-kernel timing (mpn_set_profiling): every launcher marks the stream before each kernel it launches.
+constexpr int kMaxMarks = 24;
+struct Profiler {
+    bool on;
+    int n;
+    cudaEvent_t ev[kMaxMarks + 1];
+    const char *name[kMaxMarks];
+};
+extern thread_local Profiler *g_prof;
+inline void prof_mark(cudaStream_t s, const char *name)
+{
+    Profiler *p = g_prof;
+    if (p && p->on && p->n < kMaxMarks) {
+        cudaEventRecord(p->ev[p->n], s);
+        p->name[p->n++] = name;
+    }
+}
+
 // ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s);

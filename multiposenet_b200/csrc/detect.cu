@@ -300,18 +300,22 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
         attr_set = true;
     }
     int launches = 0;
+    prof_mark(s, "detect_reset");
     detect_reset_kernel<<<(a.B + 255) / 256, 256, 0, s>>>(a.cand_count, a.done_counter, a.B);
     ++launches;
     if (a.cls) {
         const long long total = (long long)a.B * t.num_anchors;
         const long long threads = (total + 3) / 4;
         const int vec_ok = (reinterpret_cast<uintptr_t>(a.cls) % 16 == 0) ? 1 : 0;
+        prof_mark(s, "candidates_flat");
         candidates_flat_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, t.num_anchors, total, vec_ok);
     } else {
         dim3 grid((t.num_anchors + 255) / 256, a.B);
+        prof_mark(s, "candidates_nchw");
         candidates_nchw_kernel<<<grid, 256, 0, s>>>(t, a);
     }
     ++launches;
+    prof_mark(s, "sort_nms");
     sort_nms_kernel<<<a.B, kNmsThreads, smem, s>>>(t, a);
     ++launches;
     return launches;

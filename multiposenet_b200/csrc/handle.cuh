@@ -32,6 +32,8 @@ struct mpn_handle {
     int *st_num, *st_offsets;
     bool staging_ready;
     int64_t last_launches, total_launches;
+    mpn::Profiler prof;
+    bool prof_events_ready;
 };
 
 namespace mpn {

@@ -219,9 +219,11 @@ int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *s
     if (per_img < 1) per_img = 1;
     int launches = 0;
     const int nmm = B * kNK * 2;
+    prof_mark(s, "heatmap_reset");
     heatmap_reset_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(reinterpret_cast<int *>(minmax_ws), nmm);
     ++launches;
     dim3 grid(per_img, B);
+    prof_mark(s, "heatmap");
     heatmap_kernel<<<grid, kHmThreads, 0, s>>>(hml, npix, tiles, kh, seg, reinterpret_cast<int *>(minmax_ws));
     ++launches;
     if (minmax_out) {
@@ -238,6 +240,7 @@ int launch_crop(const float *kh, const float *minmax, int hh, int ww, const floa
     if (n_max <= 0) return 0;
     const int D = crop_h * crop_w * kNK;
     dim3 grid(n_max, (D + 255) / 256);
+    prof_mark(s, "crop");
     crop_kernel<<<grid, 256, 0, s>>>(kh, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32,
                                      crops_bf16);
     return 1;

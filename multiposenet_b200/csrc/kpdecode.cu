@@ -91,6 +91,7 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
 {
     if (n_max <= 0) return 0;
     if (crop_h * crop_w > kMaxPerThread * kLanes) return -(int)cudaErrorInvalidValue;
+    prof_mark(s, "keypoint_decode");
     keypoint_decode_kernel<<<n_max, kThreads, 0, s>>>(logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
     return 1;
 }

@@ -170,6 +170,7 @@ int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x,
     const size_t split_stride = (size_t)n_max * Hd;
     {
         dim3 grid(Hd / BN, m_tiles, splits);
+        prof_mark(s, "prn_fp32_fc1");
         sgemm_kernel<EPI_PARTIAL><<<grid, kThreads, 0, s>>>(x, D, w.W1, Hd, n_dev, n_host, D / splits, nullptr,
                                                             nullptr, ws.partial, split_stride);
         ++launches;
@@ -178,6 +179,7 @@ int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x,
     // fc2 + bias + ReLU + residual
     {
         dim3 grid((D + BN - 1) / BN, m_tiles, 1);
+        prof_mark(s, "prn_fp32_fc2");
         sgemm_kernel<EPI_BIAS_RELU_RESIDUAL><<<grid, kThreads, 0, s>>>(ws.y1, Hd, w.W2, D, n_dev, n_host, Hd, w.b2, x,
                                                                        logits, 0);
         ++launches;
@@ -189,6 +191,7 @@ int launch_fc1_reduce(const float *partial, int splits, size_t split_stride, con
                       const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, cudaStream_t s)
 {
     const size_t total = (size_t)m_max * hidden;
+    prof_mark(s, "prn_fc1_reduce");
     fc1_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, split_stride, bias, hidden, m_dev,
                                                                        m_host, y1, y1_bf16);
     return 1;
@@ -199,6 +202,7 @@ int launch_f32_to_bf16(const float *x, __nv_bfloat16 *y, const int *n_rows_dev, 
 {
     if (n_rows_max <= 0) return 0;
     const size_t total4 = ((size_t)n_rows_max * row_len + 3) / 4;
+    prof_mark(s, "f32_to_bf16");
     f32_to_bf16_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(x, y, n_rows_dev, n_rows_host, row_len);
     return 1;
 }

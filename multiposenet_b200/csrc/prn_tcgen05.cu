@@ -382,6 +382,7 @@ int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_
         a.m_dev = n_dev; a.m_host = n_host; a.num_k_blocks = nkb;
         a.out = ws.partial; a.split_stride = (size_t)n_max * Hd; a.ldo = Hd; a.bias = nullptr; a.residual = nullptr;
         dim3 grid(n_tiles, m_tiles, splits);
+        prof_mark(s, "prn_bf16_fc1");
         gemm_bf16_kernel<kFc1BlockN, kFc1Stages, EPI_FC1_PARTIAL, 1>
             <<<grid, kGemmThreads, SmemLayout<kFc1BlockN, kFc1Stages>::kTotal, s>>>(tm->a1, tm->b1, a);
         ++launches;
@@ -393,6 +394,7 @@ int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_
         a.m_dev = n_dev; a.m_host = n_host; a.num_k_blocks = Hd / BLOCK_K;
         a.out = logits; a.split_stride = 0; a.ldo = D; a.bias = w.b2; a.residual = x_f32;
         dim3 grid(D / kFc2BlockN, m_tiles, 1);
+        prof_mark(s, "prn_bf16_fc2");
         gemm_bf16_kernel<kFc2BlockN, kFc2Stages, EPI_FC2_RESIDUAL, 2>
             <<<grid, kGemmThreads, SmemLayout<kFc2BlockN, kFc2Stages>::kTotal, s>>>(tm->a2, tm->b2, a);
         ++launches;

@@ -414,6 +414,17 @@ class Detector:
         self._check(self._lib.mpn_test_sigmoid(self._handle, _ptr(x), _ptr(y), x.numel(), self._stream()))
         return y
 
+    def set_profiling(self, enable=True):
+        """Per-kernel CUDA-event timing of run_device / run_host_async (bench.py's roofline leg)."""
+        self._check(self._lib.mpn_set_profiling(self._handle, 1 if enable else 0))
+
+    def profile(self):
+        """[(kernel name, milliseconds)] of the most recent run (waits for it to finish)."""
+        cap = 32
+        names, ms, n = (C.c_char_p * cap)(), (C.c_float * cap)(), C.c_int32(0)
+        self._check(self._lib.mpn_get_profile(self._handle, cap, names, ms, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
     def launch_count(self):
         last, total = C.c_int64(0), C.c_int64(0)
         self._lib.mpn_launch_count(self._handle, C.byref(last), C.byref(total))

@@ -1,0 +1,393 @@
+"""GPU parity: every stage of libmpn_b200.so, called through the C ABI (ctypes, multiposenet_b200.Detector), against the
+CPU oracle (oracle/) on the same seeded inputs.
+
+Bars (BASELINE.json north_star): NMS keep sets and keypoint argmax bit-exact, integer / index work bit-exact; boxes,
+scores and fp32 PRN outputs within 1e-4 relative (the fp32-elementwise stages are in fact required to be BIT-EXACT here,
+because host and device share one exp recipe and no contraction happens on either side); bf16 PRN within 1e-2.
+Sizes are chosen so that the oracle finishes in seconds; BASELINE-size cases are covered by size-independent
+properties in test_gpu_properties.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from multiposenet_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FP32 = 1e-4      # north_star: "decoded boxes, scores and PRN outputs within 1e-4 relative (fp32)"
+RTOL_BF16 = 1e-2      # north_star: "or 1e-2 (bf16 PRN)"
+ARGMAX_GAP = 1e-5     # argmax must be exact where the top-2 logit gap exceeds accumulation noise
+
+
+def _cuda(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bit_equal(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
+    if got.dtype == np.float32:
+        bad = _bits(got) != _bits(want)
+    else:
+        bad = got != want
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} elements differ; first at {np.argwhere(bad)[0]}: " \
+                          f"{got[tuple(np.argwhere(bad)[0])]!r} vs {want[tuple(np.argwhere(bad)[0])]!r}"
+
+
+@pytest.fixture(scope="module")
+def det6(prn_weights):
+    """n_loc = 6 (the reference's anchors), capacity 8 x 640 x 640, 128 detections."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    d = Detector(prn_weights, DetectorConfig(max_batch=8, max_height=640, max_width=640, max_boxes=128))
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def det9(prn_weights):
+    """n_loc = 9 (BASELINE config 2)."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    d = Detector(prn_weights, DetectorConfig(max_batch=8, max_height=640, max_width=640, max_boxes=128,
+                                             scale_multipliers=synthetic.MULT_9))
+    yield d
+    d.close()
+
+
+# ----------------------------------------------------------------------------------------------- exp / sigmoid
+def test_device_exp_and_sigmoid_are_bit_identical_to_the_oracle(det6):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([
+        rng.normal(0, 3, 1 << 20), rng.uniform(-100, 100, 1 << 18), np.linspace(-0.01, 0.01, 4097),
+        np.array([0.0, -0.0, 1.0, -1.0, 87.0, -87.0, 88.0, 88.5, -87.5, -103.0, 1e-30, -1e-30, np.inf, -np.inf])
+    ]).astype(np.float32)
+    assert_bit_equal(det6.device_exp(_cuda(x)).cpu().numpy(), oracle.expf(x), "exp")
+    assert_bit_equal(det6.device_sigmoid(_cuda(x)).cpu().numpy(), oracle.sigmoidf(x), "sigmoid")
+    nan = det6.device_exp(_cuda(np.array([np.nan], np.float32))).cpu().numpy()
+    assert np.isnan(nan[0])
+
+
+# ----------------------------------------------------------------------------------------------- anchors
+@pytest.mark.parametrize("hw", [(128, 128), (256, 384), (512, 512), (640, 640)])
+def test_anchors_bit_exact(det6, det9, hw):
+    H, W = hw
+    assert_bit_equal(det6.anchors(H, W).cpu().numpy(), oracle.anchors(H, W), "anchors n_loc=6")
+    assert_bit_equal(det9.anchors(H, W).cpu().numpy(),
+                     oracle.anchors(H, W, multipliers=synthetic.MULT_9), "anchors n_loc=9")
+    assert det6.num_anchors(640, 640) == 51150 and det9.num_anchors(640, 640) == 76725
+
+
+# ----------------------------------------------------------------------------------------------- detect (decode + NMS)
+def _detect_case(det, wl, inputs, thr, iou, max_det):
+    anc = oracle.anchors(wl.height, wl.width, wl.strides, wl.scales, wl.multipliers, wl.ratios)
+    want = oracle.detect(inputs["class_logits"], inputs["encoded_boxes"], anc, thr, iou, max_det)
+    got = det.detect(_cuda(inputs["encoded_boxes"]), _cuda(inputs["class_logits"]), (wl.height, wl.width),
+                     score_threshold=thr, iou_threshold=iou, max_boxes=max_det)
+    got = {k: v.cpu().numpy() for k, v in got.items()}
+    assert_bit_equal(got["num_boxes"], want["num_boxes"], "num_boxes")
+    for b in range(inputs["class_logits"].shape[0]):
+        n = int(want["num_boxes"][b])
+        assert_bit_equal(got["sel_anchor"][b, :n], want["sel_anchor"][b, :n], f"keep set image {b}")
+        assert (got["sel_anchor"][b, n:] == -1).all()
+    assert_bit_equal(got["boxes"], want["boxes"], "boxes")
+    assert_bit_equal(got["scores"], want["scores"], "scores")
+    return got, want
+
+
+@pytest.mark.parametrize("key,batch", [("tiny", None), ("c1", None), ("c2_n6", 4)])
+def test_detect_bit_exact_n6(det6, key, batch):
+    wl = synthetic.WORKLOADS[key]
+    inp = synthetic.make_inputs(wl, batch=batch)
+    got, want = _detect_case(det6, wl, inp, wl.score_threshold, wl.iou_threshold, wl.max_detections)
+    assert want["num_boxes"].min() >= 1
+    assert_bit_equal(got["n_candidates"], want["n_conf"], "candidate count")
+
+
+def test_detect_bit_exact_n9_and_crowded(det9):
+    wl = synthetic.WORKLOADS["c2"]
+    _detect_case(det9, wl, synthetic.make_inputs(wl, batch=3), 0.3, 0.5, 25)
+    wl = synthetic.WORKLOADS["c3"]
+    got, want = _detect_case(det9, wl, synthetic.make_inputs(wl, batch=2), 0.3, 0.5, 128)
+    assert want["num_boxes"].max() > 60      # NMS-heavy: many kept boxes per image
+
+
+def test_detect_many_candidates_uses_the_global_sort_path(det6):
+    """A very low threshold makes > 8192 candidates per image (the shared-memory sort no longer fits) and the
+    kept list saturates at max_detections."""
+    wl = synthetic.WORKLOADS["c1"]
+    inp = synthetic.make_inputs(wl)
+    got, want = _detect_case(det6, wl, inp, 0.008, 0.5, 100)
+    assert want["n_conf"][0] > 8192 and want["num_boxes"][0] == 100
+
+
+def test_detect_edge_cases(det6):
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    A = wl.num_anchors
+    # nothing confident -> num_boxes 0, all-zero padding (nms.py:47-52)
+    cold = dict(inp, class_logits=np.full((2, A), -9.0, np.float32))
+    got, _ = _detect_case(det6, wl, cold, 0.3, 0.6, 25)
+    assert (got["num_boxes"] == 0).all() and not got["boxes"].any() and not got["scores"].any()
+    # a score exactly equal to the threshold passes nms.py:30 (>=) but is never selected by the op (strict >)
+    edge = dict(inp, class_logits=np.full((2, A), -9.0, np.float32))
+    edge["class_logits"][:, 7] = 0.0          # sigmoid(0) = 0.5 exactly
+    edge["class_logits"][:, 1000] = 2.0
+    got, want = _detect_case(det6, wl, edge, 0.5, 0.6, 25)
+    assert (got["num_boxes"] == 1).all() and (got["sel_anchor"][:, 0] == 1000).all()
+    # iou_threshold 0 and 1, max_detections 1
+    _detect_case(det6, wl, inp, 0.3, 0.0, 25)
+    _detect_case(det6, wl, inp, 0.3, 1.0, 25)
+    _detect_case(det6, wl, inp, 0.3, 0.6, 1)
+    # exact score ties: the build's rule is (score desc, anchor index asc)
+    tie = dict(inp, class_logits=np.full((2, A), -9.0, np.float32))
+    tie["class_logits"][:, [50, 20, 900, 901]] = 1.25
+    tie["encoded_boxes"] = np.zeros_like(inp["encoded_boxes"])
+    _detect_case(det6, wl, tie, 0.3, 0.6, 25)
+
+
+def test_detect_nchw_levels_equal_concatenated_layout(det6):
+    """detector/box_predictor.py:53-90 fused away: raw per-level NCHW head outputs give the same result."""
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    B, n_loc = wl.batch, wl.n_loc
+    cls_levels, box_levels, off = [], [], 0
+    for s in wl.strides:
+        gh, gw = -(-wl.height // s), -(-wl.width // s)
+        n = gh * gw * n_loc
+        c = inp["class_logits"][:, off:off + n].reshape(B, gh, gw, n_loc).transpose(0, 3, 1, 2)
+        e = inp["encoded_boxes"][:, off:off + n].reshape(B, gh, gw, n_loc * 4).transpose(0, 3, 1, 2)
+        cls_levels.append(_cuda(c))
+        box_levels.append(_cuda(e))
+        off += n
+    a = det6.detect(box_levels, cls_levels, (wl.height, wl.width), 0.3, 0.6, 25)
+    b = det6.detect(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), (wl.height, wl.width), 0.3, 0.6, 25)
+    for k in a:
+        assert_bit_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), k)
+
+
+# ----------------------------------------------------------------------------------------------- heatmaps
+@pytest.mark.parametrize("key", ["tiny", "c1"])
+def test_heatmaps_bit_exact(det6, key):
+    wl = synthetic.WORKLOADS[key]
+    hml = synthetic.make_inputs(wl)["heatmap_logits"]
+    kh, seg, mn, mx = oracle.heatmaps(hml)
+    gkh, gseg, gmm = det6.heatmaps(_cuda(hml))
+    assert_bit_equal(gkh.cpu().numpy(), kh, "keypoint_heatmaps")
+    assert_bit_equal(gseg.cpu().numpy(), seg, "segmentation_masks")
+    gmm = gmm.cpu().numpy()
+    assert_bit_equal(gmm[..., 0], mn, "min")
+    assert_bit_equal(gmm[..., 1], mx, "max")
+
+
+# ----------------------------------------------------------------------------------------------- crop_and_resize
+def test_crop_and_resize_bit_exact(det6):
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    kh, _, mn, mx = oracle.heatmaps(inp["heatmap_logits"])
+    rng = np.random.default_rng(5)
+    boxes = np.concatenate([inp["gt_boxes"][0], inp["gt_boxes"][1],
+                            np.array([[0, 0, 1, 1], [-0.2, -0.1, 0.5, 0.6], [0.5, 0.5, 1.3, 1.2], [0.3, 0.3, 0.3, 0.3],
+                                      [0.9, 0.9, 0.1, 0.1]], np.float32),
+                            rng.uniform(0, 1, (6, 4)).astype(np.float32)]).astype(np.float32)
+    ind = np.concatenate([np.zeros(len(inp["gt_boxes"][0])), np.ones(len(inp["gt_boxes"][1])),
+                          rng.integers(0, 2, 11)]).astype(np.int32)
+    mm = np.stack([mn, mx], -1)
+    want = oracle.crop_and_resize(kh, boxes, ind, (56, 36), mn, mx)
+    got = det6.crop(_cuda(kh), _cuda(boxes), _cuda(ind), _cuda(mm)).cpu().numpy()
+    assert_bit_equal(got, want, "normalised crops")
+    want = oracle.crop_and_resize(kh, boxes, ind, (56, 36))
+    got = det6.crop(_cuda(kh), _cuda(boxes), _cuda(ind)).cpu().numpy()
+    assert_bit_equal(got, want, "plain crop_and_resize")
+    assert det6.crop(_cuda(kh), _cuda(boxes[:0]), _cuda(ind[:0])).shape == (0, 56, 36, 17)
+
+
+def test_crop_weak_channel_is_zeroed_and_identity_box(det6):
+    rng = np.random.default_rng(6)
+    kh = rng.uniform(0.0, 1.0, (1, 56, 36, 17)).astype(np.float32)
+    kh[..., 3] *= 0.19                       # max <= 0.2 -> channel masked (create_pb.py:91,94)
+    mn, mx = kh.min((1, 2)), kh.max((1, 2))
+    box = np.array([[0, 0, 1, 1]], np.float32)
+    ind = np.zeros(1, np.int32)
+    got = det6.crop(_cuda(kh), _cuda(box), _cuda(ind), _cuda(np.stack([mn, mx], -1))).cpu().numpy()
+    assert not got[..., 3].any()
+    assert_bit_equal(got, oracle.crop_and_resize(kh, box, ind, (56, 36), mn, mx), "identity box, normalised")
+    plain = det6.crop(_cuda(kh), _cuda(box), _cuda(ind)).cpu().numpy()
+    assert_bit_equal(plain[0], kh[0], "box [0,0,1,1] on a 56x36 map is the identity")
+
+
+# ----------------------------------------------------------------------------------------------- PRN
+def _rel_err(got, want):
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+@pytest.mark.parametrize("n", [1, 5, 70])
+def test_prn_fp32_within_1e4(det6, prn_weights, n):
+    x = synthetic.make_crops(n, seed=11 + n)
+    want = oracle.prn(x, *prn_weights, mode=0)
+    got = det6.prn(_cuda(x), "fp32").cpu().numpy()
+    assert got.shape == x.shape
+    assert _rel_err(got, want) < RTOL_FP32
+    np.testing.assert_allclose(got, want, rtol=RTOL_FP32, atol=RTOL_FP32 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("n", [1, 5, 130])
+def test_prn_bf16_tcgen05_within_1e2_and_close_to_bf16_oracle(det6, prn_weights, n):
+    x = synthetic.make_crops(n, seed=31 + n)
+    got = det6.prn(_cuda(x), "bf16").cpu().numpy()
+    exact = oracle.prn(x, *prn_weights, mode=0)
+    assert _rel_err(got, exact) < RTOL_BF16                     # the north_star bar
+    emul = oracle.prn(x, *prn_weights, mode=1)                  # same operand rounding, fp64 accumulate
+    assert _rel_err(got, emul) < 2e-3                           # what is left is accumulation order + y1 rounding flips
+
+
+def test_prn_known_answers(prn_weights):
+    """detector/prn.py:24: zero weights -> output == input; large negative b2 -> ReLU clamps -> output == input."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    D = 56 * 36 * 17
+    x = synthetic.make_crops(3, seed=99)
+    det = Detector(None, DetectorConfig(max_batch=1, max_boxes=8))
+    try:
+        with pytest.raises(RuntimeError):
+            det.prn(_cuda(x))                                    # MPN_ERR_NO_WEIGHTS
+        det.set_prn_weights(np.zeros((D, 1024), np.float32), np.zeros(1024, np.float32),
+                            np.zeros((1024, D), np.float32), np.zeros(D, np.float32))
+        for mode in ("fp32", "bf16"):
+            assert_bit_equal(det.prn(_cuda(x), mode).cpu().numpy(), x, f"zero weights {mode}")
+        W1, b1, W2, _ = prn_weights
+        det.set_prn_weights(W1, b1, W2, np.full(D, -1e4, np.float32))
+        for mode in ("fp32", "bf16"):
+            assert_bit_equal(det.prn(_cuda(x), mode).cpu().numpy(), x, f"clamped {mode}")
+    finally:
+        det.close()
+
+
+# ----------------------------------------------------------------------------------------------- keypoint decode
+def test_keypoint_decode_argmax_bit_exact(det6, prn_weights):
+    x = synthetic.make_crops(9, seed=3)
+    logits = oracle.prn(x, *prn_weights, mode=0)
+    logits[0, :, :, 5] = 0.25                          # all-equal channel -> position (0,0), score 1/2016
+    logits[1, 40, 7, 2] = 30.0                         # dominant peak
+    logits[2, :, :, 9] = 0.0
+    logits[2, 10, 3, 9] = logits[2, 30, 30, 9] = 1.5   # exact tie -> first index
+    s, pos, arg, gap = oracle.keypoint_decode(logits)
+    gs, gpos, garg = det6.keypoint_decode(_cuda(logits))
+    assert_bit_equal(garg.cpu().numpy(), arg, "argmax")
+    assert_bit_equal(gpos.cpu().numpy(), pos, "positions")
+    np.testing.assert_allclose(gs.cpu().numpy(), s, rtol=RTOL_FP32)   # 2016-term fp32 denominator, different summation order
+    assert arg[0, 5] == 0 and abs(s[0, 5] - 1 / 2016) < 1e-9
+    assert arg[1, 2] == 40 * 36 + 7 and arg[2, 9] == 10 * 36 + 3
+
+
+def test_get_keypoints_matches_reference_golden_vectors(det6):
+    """tests/golden/get_keypoints.npz holds outputs of the reference's own inference/utils.py::get_keypoints."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "get_keypoints.npz"))
+    n = int(g["n"])
+    assert n >= 12
+    for i in range(n):
+        hm, box, thr, want = g[f"hm_{i}"], g[f"box_{i}"], float(g[f"thr_{i}"]), g[f"out_{i}"]
+        got = det6.get_keypoints(hm, box, thr)
+        assert_bit_equal(got, want.astype(np.int32), f"golden case {i}")
+        assert_bit_equal(got, oracle.get_keypoints(hm, box, thr), f"oracle case {i}")
+
+
+# ----------------------------------------------------------------------------------------------- the whole path
+def _full_case(det, wl, inp, prn_weights, mode, host):
+    thr, iou, md = wl.score_threshold, wl.iou_threshold, wl.max_detections
+    want = oracle.full_path(inp["class_logits"], inp["encoded_boxes"], inp["heatmap_logits"], wl.height, wl.width,
+                            *prn_weights, thr=thr, iou_thr=iou, max_det=md, prn_mode=1 if mode == "bf16" else 0,
+                            multipliers=wl.multipliers, ratios=wl.ratios)
+    if host:
+        bufs = det.run_host_async(inp["encoded_boxes"], inp["class_logits"], inp["heatmap_logits"],
+                                  score_threshold=thr, iou_threshold=iou, max_boxes=md, prn_mode=mode)
+        det.synchronize()
+        got = {k: v.numpy().copy() for k, v in bufs.items()}
+    else:
+        out = det.run_device(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), _cuda(inp["heatmap_logits"]),
+                             score_threshold=thr, iou_threshold=iou, max_boxes=md, prn_mode=mode)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in out.items()}
+    B = inp["class_logits"].shape[0]
+    assert_bit_equal(got["num_boxes"], want["num_boxes"], "num_boxes")
+    assert_bit_equal(got["boxes"], want["boxes"], "boxes")
+    assert_bit_equal(got["scores"], want["scores"], "scores")
+    assert_bit_equal(got["keypoint_heatmaps"], want["keypoint_heatmaps"], "keypoint_heatmaps")
+    assert_bit_equal(got["segmentation_masks"], want["segmentation_masks"], "segmentation_masks")
+    offs = np.concatenate([[0], np.cumsum(want["num_boxes"])]).astype(np.int32)
+    assert_bit_equal(got["person_offsets"], offs, "person_offsets")
+    N = int(offs[B])
+    assert N >= B
+    ks, kp = got["keypoint_scores"][:N], got["keypoint_positions"][:N]
+    decided = want["keypoint_gap"] > (ARGMAX_GAP if mode == "fp32" else 2e-2)
+    assert decided.mean() > 0.5
+    wrong = (kp != want["keypoint_positions"]).any(-1) & decided
+    assert not wrong.any(), f"{int(wrong.sum())} keypoint argmax mismatches among {int(decided.sum())} decided"
+    tol = RTOL_FP32 if mode == "fp32" else RTOL_BF16
+    np.testing.assert_allclose(ks[decided], want["keypoint_scores"][decided], rtol=50 * tol, atol=1e-7)
+    return got, want
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("host", [False, True])
+def test_full_path_tiny(det6, prn_weights, mode, host):
+    wl = synthetic.WORKLOADS["tiny"]
+    _full_case(det6, wl, synthetic.make_inputs(wl), prn_weights, mode, host)
+
+
+def test_full_path_c1_fp32(det6, prn_weights):
+    wl = synthetic.WORKLOADS["c1"]
+    _full_case(det6, wl, synthetic.make_inputs(wl), prn_weights, "fp32", False)
+
+
+def test_full_path_c2_bf16(det9, prn_weights):
+    wl = synthetic.WORKLOADS["c2"]
+    _full_case(det9, wl, synthetic.make_inputs(wl, batch=2), prn_weights, "bf16", True)
+
+
+def test_detector_call_keeps_the_reference_output_contract(det6, prn_weights):
+    """inference/detector.py:36-61 for one image: batch dimension stripped, rows filtered by score > threshold,
+    num_boxes left unfiltered."""
+    wl = synthetic.WORKLOADS["c1"]
+    inp = synthetic.make_inputs(wl)
+    from multiposenet_b200 import OUTPUT_NAMES
+    want = oracle.full_path(inp["class_logits"], inp["encoded_boxes"], inp["heatmap_logits"], 512, 512, *prn_weights,
+                            thr=0.3, iou_thr=0.6, max_det=128)
+    n = int(want["num_boxes"][0])
+    cut = float(np.median(want["scores"][0, :n]))       # a post-filter threshold that removes about half of the rows
+    out = det6(inp["encoded_boxes"], inp["class_logits"], inp["heatmap_logits"], score_threshold=cut)
+    assert sorted(out) == sorted(OUTPUT_NAMES)
+    keep = want["scores"][0, :n] > cut
+    assert 0 < keep.sum() < n
+    assert int(out["num_boxes"]) == n
+    assert_bit_equal(out["boxes"], want["boxes"][0, :n][keep], "boxes")
+    assert_bit_equal(out["scores"], want["scores"][0, :n][keep], "scores")
+    decided = want["keypoint_gap"][keep] > ARGMAX_GAP
+    assert_bit_equal(out["keypoint_positions"][decided], want["keypoint_positions"][keep][decided], "keypoint_positions")
+    assert out["keypoint_scores"].shape == (int(keep.sum()), 17)
+    assert out["keypoint_positions"].shape == (int(keep.sum()), 17, 2)
+    assert out["keypoint_heatmaps"].shape == (128, 128, 17) and out["segmentation_masks"].shape == (128, 128)
+    # same call with device tensors
+    out2 = det6(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), _cuda(inp["heatmap_logits"]),
+                score_threshold=cut)
+    for k in OUTPUT_NAMES:
+        assert_bit_equal(out2[k], out[k], k)
+
+
+def test_error_behaviour(det6):
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    with pytest.raises(ValueError):          # inference/detector.py:45
+        det6.detect(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), (200, 256))
+    with pytest.raises(ValueError):          # wrong anchor count for the image size
+        det6.detect(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), (384, 256))
+    with pytest.raises(ValueError):          # capacity
+        det6.detect(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), (256, 256), max_boxes=4096)
+    with pytest.raises(ValueError):          # host tensors on the device path
+        det6.run_device(inp["encoded_boxes"], inp["class_logits"], inp["heatmap_logits"])
+    last, total = det6.launch_count()
+    assert total > 0

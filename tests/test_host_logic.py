@@ -1,0 +1,125 @@
+"""Host-side logic that needs no GPU: synthetic workload generator, image sharding, and the world_size-2 gloo
+gather used by the multi-GPU bench (no collective on the data path)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from multiposenet_b200 import parallel, synthetic  # noqa: E402
+
+
+def test_workload_shapes_match_baseline():
+    assert synthetic.WORKLOADS["c1"].num_anchors == 32736
+    assert synthetic.WORKLOADS["c2"].num_anchors == 76725 and synthetic.WORKLOADS["c2"].n_loc == 9
+    assert synthetic.WORKLOADS["c2_n6"].num_anchors == 51150
+    assert synthetic.WORKLOADS["c4"].num_anchors == 130944
+    assert synthetic.seed_for(2, 3) == 20240203
+
+
+def test_generator_is_deterministic_and_guard_banded():
+    wl = synthetic.WORKLOADS["tiny"]
+    a = synthetic.make_inputs(wl)
+    b = synthetic.make_inputs(wl)
+    for k in ("class_logits", "encoded_boxes", "heatmap_logits"):
+        assert a[k].dtype == np.float32 and np.array_equal(a[k], b[k])
+    A = wl.num_anchors
+    assert a["class_logits"].shape == (wl.batch, A) and a["encoded_boxes"].shape == (wl.batch, A, 4)
+    assert a["heatmap_logits"].shape == (wl.batch, wl.height // 4, wl.width // 4, 18)
+    assert np.abs(a["encoded_boxes"]).max() <= 4.0
+    lt = np.log(0.3 / 0.7)
+    assert np.abs(a["class_logits"] - lt).min() > 5e-4                  # nothing near the score threshold
+    for row in a["class_logits"]:
+        conf = np.sort(row[row > lt])
+        assert conf.size >= 4 and np.diff(conf).min() > 5e-5            # confident logits are tie-free
+    # every keypoint channel has a real peak, so M != m (no 0/0 in the normalisation)
+    hm = a["heatmap_logits"][..., :17]
+    assert (hm.max(axis=(1, 2)) > 2.0).all()
+    c = synthetic.make_inputs(wl, replicate=1)
+    assert not np.array_equal(a["class_logits"], c["class_logits"])
+
+
+def test_anchor_placement_agrees_with_oracle():
+    import oracle
+    for key in ("tiny", "c2"):
+        wl = synthetic.WORKLOADS[key]
+        a = synthetic.anchors_np(wl.height, wl.width, wl.strides, wl.scales, wl.multipliers, wl.ratios)
+        b = oracle.anchors(wl.height, wl.width, wl.strides, wl.scales, wl.multipliers, wl.ratios)
+        np.testing.assert_allclose(a, b, atol=1e-6)
+
+
+def test_prn_weight_init_statistics():
+    W1, b1, W2, b2 = synthetic.make_prn_weights(d=17 * 8 * 8, hidden=64)
+    assert W1.shape == (1088, 64) and W2.shape == (64, 1088) and not b1.any() and not b2.any()
+    s1 = np.sqrt(1.0 / 1088) / 0.87962566
+    assert np.abs(W1).max() <= 2 * s1 * 1.0001 and abs(W1.std() / (s1 * 0.87962566) - 1) < 0.05
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 64, 65):
+        for w in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _fake_result(lo, hi, max_det=5):
+    rng = np.random.default_rng(100 + lo)
+    B = hi - lo
+    num = rng.integers(0, max_det + 1, B).astype(np.int32)
+    N = int(num.sum())
+    return {"boxes": rng.random((B, max_det, 4)).astype(np.float32), "scores": rng.random((B, max_det)).astype(np.float32),
+            "num_boxes": num, "keypoint_scores": np.full((N, 17), float(lo), np.float32),
+            "keypoint_positions": np.zeros((N, 17, 2), np.float32)}
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_images, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = parallel.shard_range(n_images, rank, world)
+        res = _fake_result(lo, hi)
+        merged = parallel.gather_results(res, dst=0)
+        # the bench's timing reduction: max over ranks
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == world
+        if rank == 0:
+            np.savez(out_path, **merged)
+        else:
+            assert merged is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_world_size_2_gloo_gather(tmp_path):
+    n_images, world = 7, 2
+    out = str(tmp_path / "merged.npz")
+    mp.spawn(_worker, args=(world, _free_port(), n_images, out), nprocs=world, join=True)
+    m = np.load(out)
+    parts = [_fake_result(*parallel.shard_range(n_images, r, world)) for r in range(world)]
+    assert np.array_equal(m["num_boxes"], np.concatenate([p["num_boxes"] for p in parts]))
+    assert np.array_equal(m["boxes"], np.concatenate([p["boxes"] for p in parts]))
+    assert m["person_offsets"][-1] == m["keypoint_scores"].shape[0] == sum(int(p["num_boxes"].sum()) for p in parts)
+    assert np.array_equal(np.diff(m["person_offsets"]), m["num_boxes"])
+    # persons stay in image order: the marker written by rank 1 comes after rank 0's rows
+    n0 = int(parts[0]["num_boxes"].sum())
+    assert (m["keypoint_scores"][:n0] == 0.0).all() and (m["keypoint_scores"][n0:] == 4.0).all()
