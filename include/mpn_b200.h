@@ -143,10 +143,22 @@ MPN_API int mpn_set_prn_weights(mpn_handle *h, const float *W1, const float *b1,
 MPN_API int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream);
 
 /* Same with HOST pointers for inputs and outputs: what Detector.__call__'s feed_dict / fetch does at
- * inference/detector.py:47-48.  Copies in, runs, copies out on the handle's own stream; returns after
- * enqueueing when the buffers are pinned.  mpn_synchronize waits for completion.                     */
+ * inference/detector.py:47-48.  Copy-in, the path and copy-out run on three streams of the handle, and up to
+ * MPN_HOST_DEPTH calls may be in flight (the copy-in of call i+1 overlaps the kernels of call i and the copy-out of
+ * call i-1).  mpn_submit_host returns after enqueueing (immediately when the buffers are pinned) and hands back a
+ * ticket; mpn_wait(ticket) blocks until that call's outputs are in the caller's buffers.  The caller must not touch
+ * the input and output buffers of a call before its ticket has been waited for, and must wait for ticket i before
+ * re-using its buffers for call i + MPN_HOST_DEPTH.  When encoded_boxes is pinned (cudaHostAlloc /
+ * cudaHostRegister) it is NOT copied: the NMS kernel gathers the 16-byte codes of the confident anchors in place.
+ * mpn_run_host = mpn_submit_host without a ticket; mpn_synchronize waits for everything in flight.
+ * mpn_host_traffic reports the bytes the most recent submit moved over PCIe with copy engines.              */
+#define MPN_HOST_DEPTH 3
+MPN_API int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out,
+                            int64_t *ticket);
+MPN_API int mpn_wait(mpn_handle *h, int64_t ticket);
 MPN_API int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out);
 MPN_API int mpn_synchronize(mpn_handle *h);
+MPN_API int mpn_host_traffic(const mpn_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* ---- single stages (device pointers), used by the parity tests and by the PRN-only sweep ---- */
 

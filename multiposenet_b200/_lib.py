@@ -21,6 +21,7 @@ MPN_ERR_CAPACITY = -5
 
 PRN_FP32 = 0
 PRN_BF16 = 1
+HOST_DEPTH = 3          # MPN_HOST_DEPTH
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -67,6 +68,10 @@ SYMBOLS = {
     "mpn_run": (C.c_int, [C.c_void_p, C.POINTER(MpnInputs), C.POINTER(MpnParams), C.POINTER(MpnOutputs), C.c_void_p]),
     "mpn_run_host": (C.c_int, [C.c_void_p, C.POINTER(MpnInputs), C.POINTER(MpnParams), C.POINTER(MpnOutputs)]),
     "mpn_synchronize": (C.c_int, [C.c_void_p]),
+    "mpn_submit_host": (C.c_int, [C.c_void_p, C.POINTER(MpnInputs), C.POINTER(MpnParams), C.POINTER(MpnOutputs),
+                                  C.POINTER(C.c_int64)]),
+    "mpn_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "mpn_host_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mpn_anchors": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mpn_detect": (C.c_int, [C.c_void_p, C.POINTER(MpnInputs), C.POINTER(MpnParams), C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p]),

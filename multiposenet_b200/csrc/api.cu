@@ -375,10 +375,19 @@ void mpn_destroy(mpn_handle *h)
     prn_bf16_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
                     h->kh_ws, h->minmax_ws, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
-                    h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16, h->st_cls, h->st_enc, h->st_hml,
-                    h->st_boxes, h->st_scores, h->st_seg, h->st_kscores, h->st_kpos, h->st_num, h->st_offsets};
+                    h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (HostSlot &sl : h->slots) {
+        void *sp[] = {sl.cls, sl.enc, sl.hml, sl.kh, sl.seg, sl.boxes, sl.scores, sl.kscores, sl.kpos, sl.num, sl.offsets};
+        for (void *p : sp)
+            if (p) cudaFree(p);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+    }
+    if (h->in_stream) cudaStreamDestroy(h->in_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->prof_events_ready)
         for (int i = 0; i <= kMaxMarks; ++i) cudaEventDestroy(h->prof.ev[i]);
     if (h->own_event) cudaEventDestroy(h->own_event);
@@ -561,26 +570,43 @@ static int ensure_staging(mpn_handle *h)
 {
     if (h->staging_ready) return MPN_OK;
     const size_t B = h->cfg.max_batch, A = h->max_anchors, P = h->max_hm_pix, NP = h->max_persons;
-    MPN_CUDA(h, dalloc(&h->st_cls, B * A));
-    MPN_CUDA(h, dalloc(&h->st_enc, B * A * 4));
-    MPN_CUDA(h, dalloc(&h->st_hml, B * P * 18));
-    MPN_CUDA(h, dalloc(&h->st_boxes, NP * 4));
-    MPN_CUDA(h, dalloc(&h->st_scores, NP));
-    MPN_CUDA(h, dalloc(&h->st_seg, B * P));
-    MPN_CUDA(h, dalloc(&h->st_kscores, NP * 17));
-    MPN_CUDA(h, dalloc(&h->st_kpos, NP * 34));
-    MPN_CUDA(h, dalloc(&h->st_num, B));
-    MPN_CUDA(h, dalloc(&h->st_offsets, B + 1));
+    MPN_CUDA(h, cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+    MPN_CUDA(h, cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < kHostSlots; ++k) {
+        HostSlot &sl = h->slots[k];
+        MPN_CUDA(h, dalloc(&sl.cls, B * A));
+        MPN_CUDA(h, dalloc(&sl.hml, B * P * 18));
+        MPN_CUDA(h, dalloc(&sl.kh, B * P * 17));
+        MPN_CUDA(h, dalloc(&sl.seg, B * P));
+        MPN_CUDA(h, dalloc(&sl.boxes, NP * 4));
+        MPN_CUDA(h, dalloc(&sl.scores, NP));
+        MPN_CUDA(h, dalloc(&sl.kscores, NP * 17));
+        MPN_CUDA(h, dalloc(&sl.kpos, NP * 34));
+        MPN_CUDA(h, dalloc(&sl.num, B));
+        MPN_CUDA(h, dalloc(&sl.offsets, B + 1));
+        MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+        MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+    }
     h->staging_ready = true;
     return MPN_OK;
 }
 
-int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out)
+// Device-visible alias of a host buffer that the GPU can read in place (pinned / registered memory), else NULL.
+static const float *mapped_alias(const float *host)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return static_cast<const float *>(at.devicePointer);
+    return nullptr;
+}
+
+int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, int64_t *ticket)
 {
     if (!h) return MPN_ERR_INVALID_ARGUMENT;
     if (!in || !p || !out) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs/params/outputs is NULL");
     if (!in->class_logits || !in->encoded_boxes || !in->heatmap_logits)
-        return fail(h, MPN_ERR_INVALID_ARGUMENT, "mpn_run_host takes the concatenated layout: class_logits, encoded_boxes, heatmap_logits");
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "the host path takes the concatenated layout: class_logits, encoded_boxes, heatmap_logits");
     if (!out->boxes || !out->scores || !out->num_boxes || !out->keypoint_scores || !out->keypoint_positions)
         return fail(h, MPN_ERR_INVALID_ARGUMENT, "output pointer is NULL");
     int rc = check_image_size(h, in->batch, in->height, in->width);
@@ -590,42 +616,94 @@ int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     rc = ensure_staging(h);
     if (rc) return rc;
-    cudaStream_t s = h->own_stream;
+    HostSlot &sl = h->slots[h->next_ticket % kHostSlots];
     const size_t B = in->batch, A = count_anchors(h->cfg, in->height, in->width);
     const size_t P = (size_t)(in->height / 4) * (in->width / 4), NP = B * p->max_detections;
-    // feed (inference/detector.py:47)
-    MPN_CUDA(h, cudaMemcpyAsync(h->st_cls, in->class_logits, B * A * 4, cudaMemcpyHostToDevice, s));
-    MPN_CUDA(h, cudaMemcpyAsync(h->st_enc, in->encoded_boxes, B * A * 16, cudaMemcpyHostToDevice, s));
-    MPN_CUDA(h, cudaMemcpyAsync(h->st_hml, in->heatmap_logits, B * P * 72, cudaMemcpyHostToDevice, s));
+    // ---- feed (inference/detector.py:47) on the copy-in stream.  The box codes are only ever gathered for the few
+    // hundred confident anchors, so when the caller's buffer is pinned the NMS kernel reads those 16-byte rows in
+    // place over PCIe instead of copying all B*A*16 bytes.
+    cudaStream_t si = h->in_stream, sc = h->own_stream, so = h->out_stream;
+    if (sl.used) MPN_CUDA(h, cudaStreamWaitEvent(si, sl.ev_out, 0));     // slot drained by its previous call
+    MPN_CUDA(h, cudaMemcpyAsync(sl.cls, in->class_logits, B * A * 4, cudaMemcpyHostToDevice, si));
+    MPN_CUDA(h, cudaMemcpyAsync(sl.hml, in->heatmap_logits, B * P * 72, cudaMemcpyHostToDevice, si));
+    const float *enc = mapped_alias(in->encoded_boxes);
+    h->last_h2d_bytes = (int64_t)(B * A * 4 + B * P * 72);
+    if (!enc) {
+        if (!sl.enc) MPN_CUDA(h, dalloc(&sl.enc, (size_t)h->cfg.max_batch * h->max_anchors * 4));
+        MPN_CUDA(h, cudaMemcpyAsync(sl.enc, in->encoded_boxes, B * A * 16, cudaMemcpyHostToDevice, si));
+        enc = sl.enc;
+        h->last_h2d_bytes += (int64_t)(B * A * 16);
+    }
+    MPN_CUDA(h, cudaEventRecord(sl.ev_in, si));
+    // ---- the path on the compute stream
+    MPN_CUDA(h, cudaStreamWaitEvent(sc, sl.ev_in, 0));
     mpn_inputs din = *in;
-    din.class_logits = h->st_cls; din.encoded_boxes = h->st_enc; din.heatmap_logits = h->st_hml;
+    din.class_logits = sl.cls; din.encoded_boxes = enc; din.heatmap_logits = sl.hml;
     din.level_class = nullptr; din.level_boxes = nullptr;
     mpn_outputs dout;
-    dout.boxes = h->st_boxes; dout.scores = h->st_scores; dout.num_boxes = h->st_num;
-    dout.keypoint_heatmaps = h->kh_ws; dout.segmentation_masks = out->segmentation_masks ? h->st_seg : nullptr;
-    dout.keypoint_scores = h->st_kscores; dout.keypoint_positions = h->st_kpos; dout.person_offsets = h->st_offsets;
-    rc = mpn_run(h, &din, p, &dout, s);
+    dout.boxes = sl.boxes; dout.scores = sl.scores; dout.num_boxes = sl.num;
+    dout.keypoint_heatmaps = sl.kh; dout.segmentation_masks = out->segmentation_masks ? sl.seg : nullptr;
+    dout.keypoint_scores = sl.kscores; dout.keypoint_positions = sl.kpos; dout.person_offsets = sl.offsets;
+    rc = mpn_run(h, &din, p, &dout, sc);
     if (rc) return rc;
-    // fetch (inference/detector.py:48)
-    MPN_CUDA(h, cudaMemcpyAsync(out->boxes, h->st_boxes, NP * 16, cudaMemcpyDeviceToHost, s));
-    MPN_CUDA(h, cudaMemcpyAsync(out->scores, h->st_scores, NP * 4, cudaMemcpyDeviceToHost, s));
-    MPN_CUDA(h, cudaMemcpyAsync(out->num_boxes, h->st_num, B * 4, cudaMemcpyDeviceToHost, s));
-    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_scores, h->st_kscores, NP * 17 * 4, cudaMemcpyDeviceToHost, s));
-    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_positions, h->st_kpos, NP * 34 * 4, cudaMemcpyDeviceToHost, s));
-    if (out->person_offsets)
-        MPN_CUDA(h, cudaMemcpyAsync(out->person_offsets, h->st_offsets, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
-    if (out->keypoint_heatmaps)
-        MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_heatmaps, h->kh_ws, B * P * 68, cudaMemcpyDeviceToHost, s));
-    if (out->segmentation_masks)
-        MPN_CUDA(h, cudaMemcpyAsync(out->segmentation_masks, h->st_seg, B * P * 4, cudaMemcpyDeviceToHost, s));
+    MPN_CUDA(h, cudaEventRecord(sl.ev_comp, sc));
+    // ---- fetch (inference/detector.py:48) on the copy-out stream
+    MPN_CUDA(h, cudaStreamWaitEvent(so, sl.ev_comp, 0));
+    MPN_CUDA(h, cudaMemcpyAsync(out->boxes, sl.boxes, NP * 16, cudaMemcpyDeviceToHost, so));
+    MPN_CUDA(h, cudaMemcpyAsync(out->scores, sl.scores, NP * 4, cudaMemcpyDeviceToHost, so));
+    MPN_CUDA(h, cudaMemcpyAsync(out->num_boxes, sl.num, B * 4, cudaMemcpyDeviceToHost, so));
+    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_scores, sl.kscores, NP * 17 * 4, cudaMemcpyDeviceToHost, so));
+    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_positions, sl.kpos, NP * 34 * 4, cudaMemcpyDeviceToHost, so));
+    h->last_d2h_bytes = (int64_t)(NP * (16 + 4 + 68 + 136) + B * 4);
+    if (out->person_offsets) {
+        MPN_CUDA(h, cudaMemcpyAsync(out->person_offsets, sl.offsets, (B + 1) * 4, cudaMemcpyDeviceToHost, so));
+        h->last_d2h_bytes += (int64_t)((B + 1) * 4);
+    }
+    if (out->keypoint_heatmaps) {
+        MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_heatmaps, sl.kh, B * P * 68, cudaMemcpyDeviceToHost, so));
+        h->last_d2h_bytes += (int64_t)(B * P * 68);
+    }
+    if (out->segmentation_masks) {
+        MPN_CUDA(h, cudaMemcpyAsync(out->segmentation_masks, sl.seg, B * P * 4, cudaMemcpyDeviceToHost, so));
+        h->last_d2h_bytes += (int64_t)(B * P * 4);
+    }
+    MPN_CUDA(h, cudaEventRecord(sl.ev_out, so));
+    sl.used = true;
+    if (ticket) *ticket = h->next_ticket;
+    ++h->next_ticket;
     return MPN_OK;
+}
+
+int mpn_wait(mpn_handle *h, int64_t ticket)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (ticket < 0 || ticket >= h->next_ticket) return fail(h, MPN_ERR_INVALID_ARGUMENT, "unknown ticket %lld", (long long)ticket);
+    // if the slot has been re-used since, this waits for the later call, which is ordered after this one
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    MPN_CUDA(h, cudaEventSynchronize(h->slots[ticket % kHostSlots].ev_out));
+    return MPN_OK;
+}
+
+int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out)
+{
+    return mpn_submit_host(h, in, p, out, nullptr);
 }
 
 int mpn_synchronize(mpn_handle *h)
 {
     if (!h) return MPN_ERR_INVALID_ARGUMENT;
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->staging_ready) MPN_CUDA(h, cudaStreamSynchronize(h->in_stream));
     MPN_CUDA(h, cudaStreamSynchronize(h->own_stream));
+    if (h->staging_ready) MPN_CUDA(h, cudaStreamSynchronize(h->out_stream));
+    return MPN_OK;
+}
+
+int mpn_host_traffic(const mpn_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = h->last_d2h_bytes;
     return MPN_OK;
 }
 

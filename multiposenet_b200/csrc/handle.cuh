@@ -2,6 +2,17 @@
 #pragma once
 #include "common.cuh"
 
+namespace mpn {
+constexpr int kHostSlots = 3;
+// Device staging of one in-flight host call.
+struct HostSlot {
+    float *cls, *enc, *hml, *kh, *seg, *boxes, *scores, *kscores, *kpos;
+    int *num, *offsets;
+    cudaEvent_t ev_in, ev_comp, ev_out;
+    bool used;
+};
+}  // namespace mpn
+
 struct mpn_handle {
     mpn_config cfg;
     int D;                  // crop_h * crop_w * num_keypoints
@@ -27,10 +38,12 @@ struct mpn_handle {
     mpn::PrnWorkspace prn_ws;
     void *tmaps;            // opaque: prn_tcgen05.cu
     bool have_weights;
-    // device staging for mpn_run_host
-    float *st_cls, *st_enc, *st_hml, *st_boxes, *st_scores, *st_seg, *st_kscores, *st_kpos;
-    int *st_num, *st_offsets;
+    // host path (mpn_submit_host): kHostSlots calls in flight, copy-in / compute / copy-out on three streams
+    mpn::HostSlot slots[mpn::kHostSlots];
+    cudaStream_t in_stream, out_stream;
     bool staging_ready;
+    int64_t next_ticket;
+    int64_t last_h2d_bytes, last_d2h_bytes;
     int64_t last_launches, total_launches;
     mpn::Profiler prof;
     bool prof_events_ready;

@@ -108,6 +108,7 @@ class Detector:
         self.device = torch.device("cuda", cfg.device)
         self.D = cfg.crop_size[0] * cfg.crop_size[1] * 17
         self._host_out = None
+        self._next_slot = 0
         self._dev_out = {}
         if prn_weights is not None:
             self.set_prn_weights(*prn_weights)
@@ -244,12 +245,15 @@ class Detector:
         return out
 
     # ------------------------------------------------------------------ host path (feed_dict / fetch semantics)
-    def _host_outputs(self, B, H, W, max_det):
+    def _host_outputs(self, B, H, W, max_det, slot):
         key = (B, H, W, max_det)
         if self._host_out is None or self._host_out[0] != key:
+            self._host_out = (key, {})
+        ring = self._host_out[1]
+        if slot not in ring:
             h4, w4, NP = H // 4, W // 4, B * max_det
             pin = dict(pin_memory=True)
-            bufs = {
+            ring[slot] = {
                 "boxes": torch.zeros((B, max_det, 4), dtype=torch.float32, **pin),
                 "scores": torch.zeros((B, max_det), dtype=torch.float32, **pin),
                 "num_boxes": torch.zeros((B,), dtype=torch.int32, **pin),
@@ -259,29 +263,46 @@ class Detector:
                 "keypoint_positions": torch.zeros((NP, 17, 2), dtype=torch.float32, **pin),
                 "person_offsets": torch.zeros((B + 1,), dtype=torch.int32, **pin),
             }
-            self._host_out = (key, bufs)
-        return self._host_out[1]
+        return ring[slot]
 
-    def run_host_async(self, encoded_boxes, class_logits, heatmap_logits, image_hw=None, score_threshold=None,
-                       iou_threshold=None, max_boxes=None, prn_mode=None, return_heatmaps=True):
-        """Enqueue copy-in, the path and copy-out on the handle's stream (inference/detector.py:47-48).
-        Host inputs (numpy or torch CPU, ideally pinned).  Returns the dict of pinned output buffers;
-        call synchronize() before reading them."""
+    def submit_host(self, encoded_boxes, class_logits, heatmap_logits, image_hw=None, score_threshold=None,
+                    iou_threshold=None, max_boxes=None, prn_mode=None, return_heatmaps=True):
+        """Enqueue copy-in, the path and copy-out (inference/detector.py:47-48) without waiting; up to
+        _lib.HOST_DEPTH calls may be in flight, so the PCIe copies of neighbouring calls overlap the kernels.
+        Host inputs (numpy or torch CPU, ideally pinned; they must stay untouched until wait()).  Returns
+        (ticket, dict of pinned output buffers); the buffers of ticket t are re-used by ticket t + HOST_DEPTH."""
         inp, keep, B, H, W = self._inputs(encoded_boxes, class_logits, heatmap_logits, image_hw)
         self._validate(encoded_boxes, class_logits, heatmap_logits, B, H, W, want_cuda=False)
         p = self._params(score_threshold, iou_threshold, max_boxes, prn_mode)
-        out = self._host_outputs(B, H, W, p.max_detections)
+        out = self._host_outputs(B, H, W, p.max_detections, self._next_slot)
+        self._next_slot = (self._next_slot + 1) % _lib.HOST_DEPTH
         o = MpnOutputs()
         for name in ("boxes", "scores", "num_boxes", "keypoint_scores", "keypoint_positions", "person_offsets"):
             setattr(o, name, _ptr(out[name]))
         if return_heatmaps:
             o.keypoint_heatmaps = _ptr(out["keypoint_heatmaps"])
             o.segmentation_masks = _ptr(out["segmentation_masks"])
-        self._check(self._lib.mpn_run_host(self._handle, C.byref(inp), C.byref(p), C.byref(o)))
-        return out
+        ticket = C.c_int64(-1)
+        self._check(self._lib.mpn_submit_host(self._handle, C.byref(inp), C.byref(p), C.byref(o), C.byref(ticket)))
+        return ticket.value, out
+
+    def wait(self, ticket):
+        """Block until the outputs of submit_host ticket `ticket` are in its host buffers."""
+        self._check(self._lib.mpn_wait(self._handle, int(ticket)))
+
+    def run_host_async(self, *args, **kwargs):
+        """submit_host without the ticket (kept for one-call-at-a-time use): returns the pinned output buffers;
+        call synchronize() before reading them."""
+        return self.submit_host(*args, **kwargs)[1]
 
     def synchronize(self):
         self._check(self._lib.mpn_synchronize(self._handle))
+
+    def host_traffic(self):
+        """(host->device, device->host) bytes the copy engines moved for the most recent host call."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._lib.mpn_host_traffic(self._handle, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     # ------------------------------------------------------------------ the reference-facing call
     def __call__(self, encoded_boxes, class_logits, heatmap_logits, image_hw=None, score_threshold=0.05,

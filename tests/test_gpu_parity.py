@@ -349,6 +349,40 @@ def test_full_path_c2_bf16(det9, prn_weights):
     _full_case(det9, wl, synthetic.make_inputs(wl, batch=2), prn_weights, "bf16", True)
 
 
+def test_host_pipeline_pinned_inputs_three_in_flight(det6, prn_weights):
+    """mpn_submit_host / mpn_wait with pinned inputs (box codes gathered in place over PCIe, never copied) and three
+    calls in flight give the same bits as one call at a time with pageable inputs (staged copies)."""
+    wl = synthetic.WORKLOADS["tiny"]
+    sets = [synthetic.make_inputs(wl, replicate=r) for r in range(5)]
+    names = ("encoded_boxes", "class_logits", "heatmap_logits")
+    ref = []
+    for s in sets:
+        bufs = det6.run_host_async(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], prn_mode="bf16")
+        det6.synchronize()
+        h2d_copy, _ = det6.host_traffic()
+        ref.append({k: v.numpy().copy() for k, v in bufs.items()})
+    pinned = [{k: torch.from_numpy(s[k]).pin_memory() for k in names} for s in sets]
+    got, pend = [], []
+    for s in pinned:
+        pend.append(det6.submit_host(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], prn_mode="bf16"))
+        if len(pend) == 3:
+            t, bufs = pend.pop(0)
+            det6.wait(t)
+            got.append({k: v.numpy().copy() for k, v in bufs.items()})
+    for t, bufs in pend:
+        det6.wait(t)
+        got.append({k: v.numpy().copy() for k, v in bufs.items()})
+    h2d_zero_copy, d2h = det6.host_traffic()
+    assert h2d_copy - h2d_zero_copy == sets[0]["encoded_boxes"].nbytes and d2h > 0
+    assert len(got) == len(ref) == 5
+    for g, r in zip(got, ref):
+        n = int(r["person_offsets"][-1])
+        for k in r:
+            rows = n if k.startswith("keypoint_s") or k.startswith("keypoint_p") else None
+            assert_bit_equal(g[k][:rows], r[k][:rows], k)
+    assert not all(np.array_equal(ref[0]["boxes"], r["boxes"]) for r in ref[1:])
+
+
 def test_detector_call_keeps_the_reference_output_contract(det6, prn_weights):
     """inference/detector.py:36-61 for one image: batch dimension stripped, rows filtered by score > threshold,
     num_boxes left unfiltered."""
