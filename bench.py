@@ -129,6 +129,7 @@ def algorithmic_bytes(kernel, wl, B, n_persons, n_cand, mode):
         "sort_nms": 8 * n_cand + 16 * n_cand + B * wl.max_detections * 20,
         "heatmap": 72 * pix * B + 72 * pix * B,
         "crop": n_persons * D * (4 + (2 if mode == "bf16" else 0)),
+        "prn_fused": 2 * D * HIDDEN * 2 + n_persons * D * (2 + 4 + 4),   # both weight matrices once, x, residual, logits
         "prn_bf16_fc1": D * HIDDEN * 2 + n_persons * D * 2,
         "prn_bf16_fc2": D * HIDDEN * 2 + n_persons * (HIDDEN * 2 + D * 4 + D * 4),
         "prn_fp32_fc1": D * HIDDEN * 4 + n_persons * D * 4,
@@ -364,7 +365,7 @@ def main():
             ab = algorithmic_bytes(name, wl, B, persons, n_cand, args.prn_mode)
             kernels[name] = {"ms": round(ms, 5), "share": round(ms / step_ms, 4),
                              "alg_bytes": ab, "gbs": None if not ab else round(ab / ms / 1e6, 1)}
-        top = max(order, key=lambda n: statistics.mean(acc[n]))
+        top = max([n for n in order if kernels[n]["alg_bytes"]], key=lambda n: statistics.mean(acc[n]))
         ab = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
         ach = ab / statistics.mean(acc[top]) / 1e6
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",

@@ -202,6 +202,11 @@ MPN_API int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n,
 MPN_API int mpn_set_profiling(mpn_handle *h, int32_t enable);
 MPN_API int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names, float *ms, int32_t *count);
 
+/* Development aid: globaltimer stamps (ns) of the phases of the most recent single-kernel PRN launch, 16 slots per CTA:
+ * 0 prologue, 1 fc1 loads issued, 2 fc1 MMAs issued, 3 fc1 accumulators complete, 4 partials stored, 5 barrier 1 passed,
+ * 8 y1 slice stored, 6 producer past barrier 2, 9 fc2 accumulators complete, 10 logits stored.  Synchronises the device. */
+MPN_API int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity, int32_t *grid_out);
+
 /* Counters of the most recent run (valid after the stream has been synchronised): number of kernels launched by the
  * last mpn_run / stage call, and the sum over calls since creation.                                       */
 MPN_API int mpn_launch_count(const mpn_handle *h, int64_t *last_call, int64_t *total);

@@ -216,8 +216,16 @@ int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const
         return launched(h, launch_prn_fp32(w, h->prn_ws, x_f32, n_dev, n_host, n_max, logits, s), first, "prn fp32");
     }
     if (!(h->cfg.prn_modes & 2)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
-    return launched(h, launch_prn_bf16(w, h->prn_ws, x_f32, x_bf16, n_dev, n_host, n_max, logits, h->tmaps, s), first,
-                    "prn bf16");
+    // <= 256 persons: one persistent kernel (prn_fused.cu); above: the tiled GEMM kernels.  The person count is only
+    // known on the device, so when the call's capacity exceeds 256 both are launched and each exits at once outside
+    // its regime.
+    if (h->fused) {
+        int rc = launched(h, launch_prn_fused(h, x_f32, n_dev, n_host, logits, s), first, "prn fused");
+        if (rc || n_max <= kPrnFusedMaxRows) return rc;
+        first = false;
+    }
+    return launched(h, launch_prn_bf16(w, h->prn_ws, x_f32, x_bf16, n_dev, n_host, n_max, logits, h->tmaps,
+                                       h->fused ? kPrnFusedMaxRows : 0, s), first, "prn bf16");
 }
 
 }  // namespace
@@ -357,6 +365,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     }
     if (cfg->prn_modes & 2) {
         int rc = prn_bf16_prepare(h);
+        if (rc == MPN_OK) rc = prn_fused_prepare(h);
         if (rc != MPN_OK) {
             snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
             mpn_destroy(h);
@@ -373,6 +382,7 @@ void mpn_destroy(mpn_handle *h)
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     prn_bf16_release(h);
+    prn_fused_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
                     h->kh_ws, h->minmax_ws, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
@@ -705,6 +715,17 @@ int mpn_host_traffic(const mpn_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes
     if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
     if (d2h_bytes) *d2h_bytes = h->last_d2h_bytes;
     return MPN_OK;
+}
+
+int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity, int32_t *grid_out)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    MPN_CUDA(h, cudaDeviceSynchronize());
+    int g = 0;
+    const int rc = prn_fused_trace(h, enable, reinterpret_cast<unsigned long long *>(host_out), capacity, &g);
+    if (grid_out) *grid_out = g;
+    return rc == MPN_OK ? MPN_OK : fail(h, rc, "fused PRN trace unavailable");
 }
 
 int mpn_set_profiling(mpn_handle *h, int32_t enable)

@@ -12,6 +12,7 @@ constexpr int kMaxLevels = MPN_MAX_LEVELS;
 constexpr int kMaxShapes = MPN_MAX_ANCHOR_SHAPES;
 constexpr int kSortSmemCap = 8192;      // candidates per image sorted in shared memory; above: global scratch
 constexpr int kMaxDetCap = 1024;        // kept boxes staged in shared memory
+constexpr int kPrnFusedMaxRows = 256;   // persons per call handled by the single-kernel PRN (prn_fused.cu)
 
 // Everything the kernels need to rebuild anchor `a` from its index (detector/anchor_generator.py:53-116)
 // without an anchor tensor in HBM.  Passed by value (~1.3 KB of kernel parameters).
@@ -104,10 +105,12 @@ struct PrnWorkspace {
 };
 int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x, const int *n_dev, int n_host,
                     int n_max, float *logits, cudaStream_t s);
+// skip_le: the launched kernels exit at once when the person count is <= skip_le (the fused kernel handles those)
 int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_f32, const __nv_bfloat16 *x_bf16,
-                    const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, cudaStream_t s);
+                    const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, int skip_le, cudaStream_t s);
 int launch_fc1_reduce(const float *partial, int splits, size_t split_stride, const float *bias, int hidden,
-                      const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, cudaStream_t s);
+                      const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, int skip_le,
+                      cudaStream_t s);
 int launch_f32_to_bf16(const float *x, __nv_bfloat16 *y, const int *n_rows_dev, int n_rows_host, int row_len,
                        int n_rows_max, cudaStream_t s);
 int launch_transpose_to_bf16(const float *w, int rows, int cols, __nv_bfloat16 *wt, cudaStream_t s);

@@ -37,6 +37,7 @@ struct mpn_handle {
     __nv_bfloat16 *W1t, *W2t;
     mpn::PrnWorkspace prn_ws;
     void *tmaps;            // opaque: prn_tcgen05.cu
+    void *fused;            // opaque: prn_fused.cu (NULL when the shape is not covered)
     bool have_weights;
     // host path (mpn_submit_host): kHostSlots calls in flight, copy-in / compute / copy-out on three streams
     mpn::HostSlot slots[mpn::kHostSlots];
@@ -52,4 +53,8 @@ struct mpn_handle {
 namespace mpn {
 int prn_bf16_prepare(mpn_handle *h);   // prn_tcgen05.cu: TMA tensor maps for the bf16 GEMMs
 void prn_bf16_release(mpn_handle *h);
+int prn_fused_prepare(mpn_handle *h);  // prn_fused.cu: persistent single-kernel PRN for <= kPrnFusedMaxRows persons
+void prn_fused_release(mpn_handle *h);
+int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int capacity, int *grid_out);
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s);
 }

@@ -1,0 +1,584 @@
+// Pose Residual Network, bf16 mode, SMALL-BATCH regime (<= 256 persons per call): ONE persistent, cooperative kernel.
+//
+// Replaces detector/prn.py:15-25 (slim.fully_connected x2 + residual):
+//   y1 = relu(x W1 + b1),  y2 = relu(y1 W2 + b2),  logits = x + y2
+//
+// Below ~210 persons the PRN is bound by the HBM stream of its 140 MB of bf16 weights, and a
+// 70 MB stream timed alone cannot beat ~16 us on a B200 (7 us of launch + ramp + tail around 9.6 us of transfer,
+// tools/stream_bench.cu).  So the two layers are NOT two kernels: one CTA per SM stays resident and the weight stream
+// never stops --
+//   phase 1  fc1: CTA (hq, z) owns hidden quarter hq (256 units) and K split z of the 34272-long reduction;
+//            TMA ring -> tcgen05.mma 128 x 256 x 16 (accumulators in TMEM) -> fp32 partial sums to L2
+//   barrier  grid-wide (all CTAs are co-resident: cooperative launch)
+//   phase 2  split-K reduce in fixed order + bias + ReLU + bf16 -> y1 (deterministic, no atomics on data)
+//   barrier
+//   phase 3  fc2: CTA t owns 240 output columns (143 tiles); A = y1 (L2-resident), B = W2 tile;
+//            epilogue logits = x + relu(acc + b2)
+// The producer warp runs ahead: while the CTA sits in the barriers / the reduce it is already pulling its first W2
+// tiles into the ring, so HBM stays busy across the phase boundaries.
+//
+// Roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) + TMEM allocation, warps 2..9 =
+// epilogue / reduce (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// Activations are fetched as 32-row TMA boxes, only as many as there are persons (M is fixed at 128 per MMA but
+// rows past the last box are never loaded; their accumulator rows are garbage and never stored).
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "common.cuh"
+#include "handle.cuh"
+#include "tcgen05_utils.cuh"
+
+namespace mpn {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kHq = 4;                                   // hidden quarters of fc1
+constexpr int kFc1N = 256, kFc2N = 240;                  // UMMA N of the two layers
+constexpr int kXBox = 32;                                // rows per activation TMA box
+constexpr int kXBoxBytes = kXBox * 128;
+constexpr int kXTileBytes = 128 * 128;                   // one 128-row activation tile (16 KB)
+constexpr int kWTileBytes = 256 * 128;                   // one weight tile (32 KB; fc2 uses 240 of the 256 rows)
+constexpr int kRingBytes = 192 * 1024;                   // stage = [W tile | X tile 0 | X tile 1 (only for > 128 persons)]
+constexpr int kMaxStages = 4;                            //   <= 128 persons: 4 stages of 48 KB, else 3 stages of 64 KB
+constexpr int kEpiWarps = 16;                           // 4 per TMEM lane quadrant: the epilogues are issue-latency bound
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 32 x 16 fp32 transpose buffers
+constexpr int kB2Offset = kStgOffset + kEpiWarps * 2048; // b2 tile of the current fc2 output tile
+constexpr int kBarOffset = kB2Offset + 1024;
+constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 2) * 8 + 16 + 1024;
+constexpr uint32_t kTmemCols = 512;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct FusedArgs {
+    const int *n_dev;
+    int n_host;
+    int D, hidden;
+    int nkb1;                // k blocks of fc1 (ceil(D / 64))
+    int nkb2;                // k blocks of fc2 (hidden / 64)
+    int splits;              // K splits of fc1
+    int tiles2;              // output tiles of fc2 (ceil(D / 240))
+    float *partial;          // [splits, rows_cap, hidden]
+    size_t split_stride;
+    const float *b1;
+    __nv_bfloat16 *y1;       // [rows, hidden]
+    const float *b2;
+    const float *x;          // fp32 crops [N, D] (residual)
+    float *logits;           // [N, D]
+    unsigned long long *arrivals;   // grid barrier: monotonically increasing arrival count (2 * grid per launch)
+    unsigned long long *trace;      // optional [grid, 16] globaltimer stamps (mpn_debug_fused_trace)
+};
+
+struct FusedMaps {
+    CUtensorMap x, w1, y1, w2;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier over a counter that is never reset: every launch that gets past the person-count check adds exactly
+// 2 * grid arrivals, so the counter value at kernel entry, rounded down to a multiple of 2 * grid, is this launch's base
+// (no CTA can see more than grid - 1 arrivals of barrier 1 before it has arrived itself).  All CTAs are co-resident
+// (cooperative launch).  One thread per CTA arrives; one round trip to L2 to arrive, one to observe.
+__device__ __forceinline__ void grid_arrive(unsigned long long *arrivals)
+{
+    // Called by ONE thread after a CTA-wide bar.sync: the barrier orders the other threads' stores before this
+    // fence, whose cumulativity publishes them at GPU scope (the cooperative-groups grid.sync pattern).
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    atomicAdd(arrivals, 1ULL);
+}
+
+__device__ __forceinline__ void grid_wait(const unsigned long long *arrivals, unsigned long long target)
+{
+    // Poll with RELAXED loads and fence once at the end: an acquire load is compiled to LDG + CCTL.IVALL, and an L1
+    // invalidation every few hundred nanoseconds disturbs the memory pipeline of the warps that are still working.
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+        unsigned long long v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(arrivals) : "memory");
+        if (v >= target) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            return;
+        }
+        __nanosleep(64);
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void stamp(const FusedArgs &a, int slot)
+{
+    if (a.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// Per-warp 32 x 16 fp32 transpose through shared memory: the accumulator arrives one ROW per lane (tcgen05.ld 32x32b.x16),
+// global memory wants one 64-byte row segment per 4 lanes.  16-byte chunks are XOR-swizzled by ((row >> 1) & 3) so that
+// both the row-per-lane writes and the 4-lanes-per-row reads are bank-conflict free.
+__device__ __forceinline__ void stage_write(float *stg, int lane, const uint32_t (&r)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4 *>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+}
+
+// i-th of the 4 coalesced passes: lane -> (row 8 i + lane / 4, columns 4 (lane % 4) ..)
+__device__ __forceinline__ float4 stage_read(const float *stg, int lane, int i)
+{
+    const int row = 8 * i + (lane >> 2), j = lane & 3;
+    return *reinterpret_cast<const float4 *>(stg + row * 16 + ((j ^ ((row >> 1) & 3)) << 2));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                 const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,
+                 const FusedArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const int N = args.n_dev ? *args.n_dev : args.n_host;
+    if (N <= 0 || N > kPrnFusedMaxRows) return;      // uniform over the grid; the general kernels take N > 256
+    const int nm = (N + 127) >> 7;                   // 128-row M tiles
+    const int nb = (N + kXBox - 1) / kXBox;          // 32-row activation boxes
+    const int G = gridDim.x, c = blockIdx.x;
+    const unsigned long long bar_base = (ld_acquire_u64(args.arrivals) / (2ull * G)) * (2ull * G);
+    const int stage_bytes = kWTileBytes + nm * kXTileBytes;
+    const int n_stages = kRingBytes / stage_bytes;   // 4 or 3
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kBarOffset);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    uint64_t *tmem_full_bar = empty_bar + kMaxStages;
+    uint64_t *tmem_empty_bar = tmem_full_bar + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_y1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(args, 0);                                   // prologue done
+
+    const bool has_fc1 = c < kHq * args.splits;
+    const int hq = c % kHq, z = c / kHq;
+    const int kb0 = has_fc1 ? (int)(((long long)z * args.nkb1) / args.splits) : 0;
+    const int kb1 = has_fc1 ? (int)(((long long)(z + 1) * args.nkb1) / args.splits) : 0;
+    const uint32_t x_bytes = (uint32_t)nb * kXBoxBytes;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ================= TMA producer =================
+            int it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int st = it % n_stages;
+                mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
+                uint8_t *stage = smem + st * stage_bytes;
+                tma_load_2d(stage, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
+                for (int b = 0; b < nb; ++b)
+                    tma_load_2d(stage + kWTileBytes + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
+            }
+            stamp(args, 1);                                                 // all fc1 loads issued
+            // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces
+            const int first2 = it;
+            int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
+            bool y1_ready = false;
+            for (int tile = c; tile < args.tiles2; tile += G) {
+                for (int kb = 0; kb < args.nkb2; ++kb, ++it) {
+                    const int st = it % n_stages;
+                    if (!y1_ready && it - first2 >= n_stages) {
+                        grid_wait(args.arrivals, bar_base + 2ull * G);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        stamp(args, 6);                                     // producer saw barrier 2
+                        y1_ready = true;
+                        for (; flushed < it; ++flushed) {      // only ever the first n_stages k blocks of the first tile
+                            uint8_t *stg = smem + (flushed % n_stages) * stage_bytes + kWTileBytes;
+                            for (int b = 0; b < nb; ++b)
+                                tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
+                                            (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
+                        }
+                    }
+                    mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc2N * 128);
+                    uint8_t *stage = smem + st * stage_bytes;
+                    tma_load_2d(stage, &tmap_w2, full_bar + st, kb * BLOCK_K, tile * kFc2N, kEvictFirst);
+                    if (y1_ready) {
+                        for (int b = 0; b < nb; ++b)
+                            tma_load_2d(stage + kWTileBytes + b * kXBoxBytes, &tmap_y1, full_bar + st, kb * BLOCK_K, b * kXBox,
+                                        kEvictLast);
+                        flushed = it + 1;
+                    }
+                }
+            }
+            if (!y1_ready && it > first2) {
+                grid_wait(args.arrivals, bar_base + 2ull * G);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                stamp(args, 6);
+                for (; flushed < it; ++flushed) {
+                    uint8_t *stg = smem + (flushed % n_stages) * stage_bytes + kWTileBytes;
+                    for (int b = 0; b < nb; ++b)
+                        tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
+                                    (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {   // ================= MMA issuer =================
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, kFc1N);
+            constexpr uint32_t idesc2 = make_idesc_bf16(128, kFc2N);
+            int it = 0, round = 0;
+            if (has_fc1) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int st = it % n_stages;
+                    mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
+                    tc_fence_after();
+                    const uint32_t s_addr = smem_u32(smem + st * stage_bytes);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(s_addr);
+                    for (int m = 0; m < nm; ++m) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(s_addr + kWTileBytes + m * kXTileBytes);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                      idesc1, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + st);
+                }
+                umma_commit(tmem_full_bar);
+                ++round;
+                stamp(args, 2);                                             // all fc1 MMAs issued
+            }
+            for (int tile = c; tile < args.tiles2; tile += G) {
+                if (round > 0) {   // the epilogue has drained the previous accumulators
+                    mbar_wait(tmem_empty_bar, ((uint32_t)(round - 1)) & 1u);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < args.nkb2; ++kb, ++it) {
+                    const int st = it % n_stages;
+                    mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
+                    tc_fence_after();
+                    const uint32_t s_addr = smem_u32(smem + st * stage_bytes);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(s_addr);
+                    for (int m = 0; m < nm; ++m) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(s_addr + kWTileBytes + m * kXTileBytes);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                      idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + st);
+                }
+                umma_commit(tmem_full_bar);
+                ++round;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue / reduce warps =================
+        // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule), column group cg = (warp - 2) / 4.  The work of these
+        // warps is short, serial and latency bound, hence many warps, 16-column chunks and addresses hoisted out of the
+        // chunk loops.
+        const int ew = warp - 2, q = warp & 3, cg = ew >> 2;
+        const int tid_e = threadIdx.x - 64;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        float *stg = reinterpret_cast<float *>(smem + kStgOffset + ew * 2048);
+        float *s_b2 = reinterpret_cast<float *>(smem + kB2Offset);
+        const int sub_row = lane >> 2, sub_col = (lane & 3) << 2;    // coalesced side of the transpose
+        int round = 0;
+        if (has_fc1) {   // ---- fc1 partial sums: partial[z][row][hq*256 + col]; this warp: columns [cg*64, +64) as 4 chunks
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+            if (tid_e == 0) stamp(args, 3);                                 // fc1 accumulators complete
+            for (int m = 0; m < nm; ++m) {
+                const int row0 = m * 128 + q * 32;
+                if (row0 >= N) break;                                       // warp-uniform: no person in these 32 rows
+                float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(row0 + sub_row) * args.hidden +
+                             hq * kFc1N + cg * 64 + sub_col;
+                const size_t row_step = (size_t)8 * args.hidden;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
+                    stage_write(stg, lane, r);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (row0 + sub_row + 8 * i < N)
+                            __stcg(reinterpret_cast<float4 *>(dst + i * row_step + ch * 16), stage_read(stg, lane, i));
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
+            ++round;
+        }
+        epi_bar_sync();
+        if (tid_e == 0) {
+            stamp(args, 4);                                                 // partial sums stored
+            grid_arrive(args.arrivals);
+            grid_wait(args.arrivals, bar_base + (unsigned long long)G);
+            stamp(args, 5);                                                 // barrier 1 passed
+        }
+        epi_bar_sync();
+        {   // ---- y1 = relu(sum_z partial + b1) in bf16: this CTA's slice of the N x hidden outputs, float4 at a time.
+            // Four threads per output vector, each with its <= 10 partial loads in flight at once (one L2 round trip),
+            // then a fixed-order combine ((s0 + s1) + (s2 + s3)): deterministic, no atomics on data.
+            const int vec_per_row = args.hidden >> 2;
+            const int total = N * vec_per_row;
+            const int per = (total + G - 1) / G;
+            const int v_end = min(total, (c + 1) * per);
+            const int s_quarter = (args.splits + 3) >> 2;                  // <= 10 (splits <= 40)
+            const int part = tid_e & 3;
+            const int s_lo = part * s_quarter, s_hi = min(args.splits, s_lo + s_quarter);
+            for (int v0 = c * per; v0 < v_end; v0 += kEpiWarps * 8) {
+                const int v = v0 + (tid_e >> 2);
+                const bool live = v < v_end;
+                const int row = live ? v / vec_per_row : 0, c4 = live ? v - row * vec_per_row : 0;
+                const float *src = args.partial + (size_t)s_lo * args.split_stride + (size_t)row * args.hidden + c4 * 4;
+                float4 pv[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i)
+                    pv[i] = (live && s_lo + i < s_hi) ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t)i * args.split_stride))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 acc = pv[0];
+#pragma unroll
+                for (int i = 1; i < 10; ++i) {
+                    if (s_lo + i < s_hi) {
+                        acc.x = __fadd_rn(acc.x, pv[i].x); acc.y = __fadd_rn(acc.y, pv[i].y);
+                        acc.z = __fadd_rn(acc.z, pv[i].z); acc.w = __fadd_rn(acc.w, pv[i].w);
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {                          // lanes 4k..4k+3 hold the four partial sums
+                    float4 oth;
+                    oth.x = __shfl_xor_sync(0xffffffffu, acc.x, o); oth.y = __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    oth.z = __shfl_xor_sync(0xffffffffu, acc.z, o); oth.w = __shfl_xor_sync(0xffffffffu, acc.w, o);
+                    // the lower lane of each pair adds (its own) + (the upper one's): a fixed association
+                    if ((part & o) == 0) {
+                        acc.x = __fadd_rn(acc.x, oth.x); acc.y = __fadd_rn(acc.y, oth.y);
+                        acc.z = __fadd_rn(acc.z, oth.z); acc.w = __fadd_rn(acc.w, oth.w);
+                    }
+                }
+                if (live && part == 0) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(args.b1 + c4 * 4));
+                    acc.x = fmaxf(__fadd_rn(acc.x, bb.x), 0.0f);
+                    acc.y = fmaxf(__fadd_rn(acc.y, bb.y), 0.0f);
+                    acc.z = fmaxf(__fadd_rn(acc.z, bb.z), 0.0f);
+                    acc.w = fmaxf(__fadd_rn(acc.w, bb.w), 0.0f);
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+                    uint2 o;
+                    o.x = *reinterpret_cast<const unsigned *>(&lo);
+                    o.y = *reinterpret_cast<const unsigned *>(&hi);
+                    __stcg(reinterpret_cast<uint2 *>(args.y1 + (size_t)row * args.hidden + c4 * 4), o);
+                }
+            }
+        }
+        epi_bar_sync();
+        if (tid_e == 0) {
+            stamp(args, 8);                                                 // y1 slice stored
+            grid_arrive(args.arrivals);
+        }
+        // ---- fc2 epilogue: logits = x + relu(acc + b2)   (detector/prn.py:22,24)
+        // This warp: columns [cg*64, +64) of the 240-column tile as 4 chunks of 16 (the last group has 3).  Chunks go
+        // through the per-warp transpose so that the residual loads and the logit stores are 64-byte row segments.  The
+        // residual does not depend on the GEMM: it is fetched BEFORE waiting for the accumulator.
+        for (int tile = c; tile < args.tiles2; tile += G) {
+            const int n0 = tile * kFc2N;
+            if (tid_e < kFc2N / 4) {
+                const int n = n0 + tid_e * 4;
+                reinterpret_cast<float4 *>(s_b2)[tid_e] =
+                    n < args.D ? __ldg(reinterpret_cast<const float4 *>(args.b2 + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int m = 0; m < nm; ++m) {
+                const int row0 = m * 128 + q * 32;
+                const bool rows_live = row0 < N;                            // warp-uniform
+                const int col_base = cg * 64 + sub_col;                     // column of this lane inside the tile, chunk 0
+                const size_t off = (size_t)(row0 + sub_row) * args.D + n0 + col_base;
+                const size_t row_step = (size_t)8 * args.D;
+                float4 xr[4][4];                                            // [chunk][pass]
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const bool col_ok = rows_live && col_base + ch * 16 < kFc2N && n0 + col_base + ch * 16 < args.D;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        xr[ch][i] = (col_ok && row0 + sub_row + 8 * i < N)
+                                        ? __ldcg(reinterpret_cast<const float4 *>(args.x + off + i * row_step + ch * 16))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (m == 0) {
+                    epi_bar_sync();                                         // s_b2 visible
+                    mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
+                    tc_fence_after();
+                    if (tid_e == 0) stamp(args, 9);                         // fc2 accumulators complete
+                }
+                if (!rows_live) continue;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (cg * 64 + ch * 16 >= kFc2N) break;                  // warp-uniform (last column group: 3 chunks)
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
+                    stage_write(stg, lane, r);
+                    __syncwarp();
+                    if (n0 + col_base + ch * 16 < args.D) {
+                        const float4 b = *reinterpret_cast<const float4 *>(s_b2 + col_base + ch * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (row0 + sub_row + 8 * i < N) {
+                                const float4 a = stage_read(stg, lane, i);
+                                float4 o;
+                                o.x = __fadd_rn(xr[ch][i].x, fmaxf(__fadd_rn(a.x, b.x), 0.0f));
+                                o.y = __fadd_rn(xr[ch][i].y, fmaxf(__fadd_rn(a.y, b.y), 0.0f));
+                                o.z = __fadd_rn(xr[ch][i].z, fmaxf(__fadd_rn(a.z, b.z), 0.0f));
+                                o.w = __fadd_rn(xr[ch][i].w, fmaxf(__fadd_rn(a.w, b.w), 0.0f));
+                                __stcs(reinterpret_cast<float4 *>(args.logits + off + i * row_step + ch * 16), o);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
+            ++round;
+            if (tid_e == 0) stamp(args, 15);                                // warp 2 finished the fc2 epilogue
+            epi_bar_sync();                                                 // s_b2 may be overwritten by the next tile
+        }
+        if (tid_e == 0) stamp(args, 10);                                    // logits stored
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+struct FusedState {
+    FusedMaps maps;
+    float *partial;
+    size_t split_stride;
+    unsigned long long *bar;   // grid barrier arrival counter
+    unsigned long long *trace;
+    int grid, splits, rows_cap;
+};
+
+int prn_fused_prepare(mpn_handle *h)
+{
+    const int D = h->D, Hd = h->cfg.prn_hidden;
+    if (Hd != kHq * kFc1N || D % 16 != 0) return MPN_OK;   // shape not covered: the general kernels are used alone
+    int dev = h->cfg.device, sms = 0, coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || sms < kHq) return MPN_OK;
+    if (cudaFuncSetAttribute(prn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel, kThreads, kSmemBytes) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        snprintf(h->err, sizeof(h->err), "prn_fused_kernel cannot be made resident (smem %d)", kSmemBytes);
+        return MPN_ERR_CUDA;
+    }
+    FusedState *st = new FusedState;
+    memset(st, 0, sizeof(*st));
+    st->grid = sms;
+    st->splits = sms / kHq;
+    const int nkb1 = (D + BLOCK_K - 1) / BLOCK_K;
+    if (st->splits > nkb1) st->splits = nkb1;
+    if (st->splits > 40) st->splits = 40;            // the reduce keeps <= 20 partial loads per thread in flight
+    st->rows_cap = h->prn_ws.n_max < kPrnFusedMaxRows ? h->prn_ws.n_max : kPrnFusedMaxRows;
+    st->split_stride = (size_t)st->rows_cap * Hd;
+    const uint64_t rows = (uint64_t)h->prn_ws.n_max;
+    bool ok = cudaMalloc(&st->partial, (size_t)st->splits * st->split_stride * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&st->bar, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(st->bar, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && encode_2d(&st->maps.x, h->crops_bf16, rows, (uint64_t)D, kXBox) &&
+         encode_2d(&st->maps.w1, h->W1t, (uint64_t)Hd, (uint64_t)D, kFc1N) &&
+         encode_2d(&st->maps.y1, h->prn_ws.y1_bf16, rows, (uint64_t)Hd, kXBox) &&
+         encode_2d(&st->maps.w2, h->W2t, (uint64_t)D, (uint64_t)Hd, kFc2N);
+    if (!ok) {
+        cudaGetLastError();
+        if (st->partial) cudaFree(st->partial);
+        if (st->bar) cudaFree(st->bar);
+        delete st;
+        snprintf(h->err, sizeof(h->err), "fused PRN setup failed (allocation or cuTensorMapEncodeTiled)");
+        return MPN_ERR_CUDA;
+    }
+    h->fused = st;
+    return MPN_OK;
+}
+
+void prn_fused_release(mpn_handle *h)
+{
+    FusedState *st = static_cast<FusedState *>(h->fused);
+    if (!st) return;
+    cudaFree(st->partial);
+    cudaFree(st->bar);
+    if (st->trace) cudaFree(st->trace);
+    delete st;
+    h->fused = nullptr;
+}
+
+// Development aid: per-CTA globaltimer stamps of the phases of the most recent fused launch (16 slots per CTA).
+int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int capacity, int *grid_out)
+{
+    FusedState *st = static_cast<FusedState *>(h->fused);
+    if (!st) return MPN_ERR_UNSUPPORTED;
+    if (enable && !st->trace) {
+        if (cudaMalloc(&st->trace, (size_t)st->grid * 16 * sizeof(unsigned long long)) != cudaSuccess) return MPN_ERR_CUDA;
+        cudaMemset(st->trace, 0, (size_t)st->grid * 16 * sizeof(unsigned long long));
+    }
+    if (host_out && st->trace) {
+        const int n = capacity < st->grid * 16 ? capacity : st->grid * 16;
+        if (cudaMemcpy(host_out, st->trace, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return MPN_ERR_CUDA;
+    }
+    if (grid_out) *grid_out = st->grid;
+    if (!enable && st->trace) { cudaFree(st->trace); st->trace = nullptr; }
+    return MPN_OK;
+}
+
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s)
+{
+    FusedState *st = static_cast<FusedState *>(h->fused);
+    if (!st) return -(int)cudaErrorInvalidValue;
+    FusedArgs a;
+    a.n_dev = n_dev; a.n_host = n_host;
+    a.D = h->D; a.hidden = h->cfg.prn_hidden;
+    a.nkb1 = (h->D + BLOCK_K - 1) / BLOCK_K;
+    a.nkb2 = h->cfg.prn_hidden / BLOCK_K;
+    a.splits = st->splits;
+    a.tiles2 = (h->D + kFc2N - 1) / kFc2N;
+    a.partial = st->partial; a.split_stride = st->split_stride;
+    a.b1 = h->b1; a.y1 = h->prn_ws.y1_bf16; a.b2 = h->b2; a.x = x_f32; a.logits = logits;
+    a.arrivals = st->bar;
+    a.trace = st->trace;
+    void *params[] = {&st->maps.x, &st->maps.w1, &st->maps.y1, &st->maps.w2, &a};
+    prof_mark(s, "prn_fused");
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(prn_fused_kernel), dim3(st->grid),
+                                                dim3(kThreads), params, (size_t)kSmemBytes, s);
+    if (e != cudaSuccess) return -(int)e;
+    return 1;
+}
+
+}  // namespace mpn

@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(256) fc1_reduce_kernel(const float *__restrict
                                                          const size_t split_stride, const float *__restrict__ bias,
                                                          const int hidden, const int *__restrict__ m_dev,
                                                          const int m_host, float *__restrict__ y1,
-                                                         __nv_bfloat16 *__restrict__ y1_bf16)
+                                                         __nv_bfloat16 *__restrict__ y1_bf16, const int skip_le)
 {
     const int M = m_dev ? *m_dev : m_host;
+    if (M <= skip_le) return;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)M * hidden) return;
     float s = partial[i];
@@ -174,7 +175,7 @@ int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x,
         sgemm_kernel<EPI_PARTIAL><<<grid, kThreads, 0, s>>>(x, D, w.W1, Hd, n_dev, n_host, D / splits, nullptr,
                                                             nullptr, ws.partial, split_stride);
         ++launches;
-        launches += launch_fc1_reduce(ws.partial, splits, split_stride, w.b1, Hd, n_dev, n_host, n_max, ws.y1, nullptr, s);
+        launches += launch_fc1_reduce(ws.partial, splits, split_stride, w.b1, Hd, n_dev, n_host, n_max, ws.y1, nullptr, 0, s);
     }
     // fc2 + bias + ReLU + residual
     {
@@ -188,12 +189,13 @@ int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x,
 }
 
 int launch_fc1_reduce(const float *partial, int splits, size_t split_stride, const float *bias, int hidden,
-                      const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, cudaStream_t s)
+                      const int *m_dev, int m_host, int m_max, float *y1, __nv_bfloat16 *y1_bf16, int skip_le,
+                      cudaStream_t s)
 {
     const size_t total = (size_t)m_max * hidden;
     prof_mark(s, "prn_fc1_reduce");
     fc1_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, split_stride, bias, hidden, m_dev,
-                                                                       m_host, y1, y1_bf16);
+                                                                       m_host, y1, y1_bf16, skip_le);
     return 1;
 }
 

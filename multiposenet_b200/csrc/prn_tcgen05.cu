@@ -25,20 +25,18 @@
 
 #include "common.cuh"
 #include "handle.cuh"
+#include "tcgen05_utils.cuh"
 
 namespace mpn {
 
 namespace {
 
+using namespace tc;
+
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2..5 epilogue
 constexpr int kFc1BlockN = 128, kFc1Stages = 6;
 constexpr int kFc2BlockN = 96, kFc2Stages = 3;
-
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // streamed once: weights
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // re-read by every N tile: activations
 
 enum { EPI_FC1_PARTIAL = 0, EPI_FC2_RESIDUAL = 1 };
 
@@ -51,105 +49,12 @@ struct GemmArgs {
     int ldo;
     const float *bias;       // fc2
     const float *residual;   // fc2: x [M, N]
+    int skip_le;             // exit when M <= skip_le (those calls are served by prn_fused.cu)
 };
 
 struct TensorMaps {
     CUtensorMap a1, b1, a2, b2;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
-                                            uint64_t hint)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
-        : "memory");
-}
-
-// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address          bits [0, 14)
-    d |= (uint64_t)1 << 16;                         // leading byte offset    bits [16, 30) (unused with swizzle)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset     bits [32, 46)
-    d |= (uint64_t)1 << 46;                         // descriptor version 1   bits [46, 48)
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B           bits [61, 64)
-    return d;
-}
-
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    // the "+r" operands tie every later use of r[] to the completion of the asynchronous load
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
 
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
@@ -173,7 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     const int M = args.m_dev ? *args.m_dev : args.m_host;
     const int m0 = blockIdx.y * BLOCK_M;
-    if (m0 >= M) return;                       // uniform per CTA, before any barrier or TMEM allocation
+    if (m0 >= M || M <= args.skip_le) return;  // uniform per CTA, before any barrier or TMEM allocation
     const int n0 = blockIdx.x * BLOCK_N;
     const int splits = gridDim.z, z = blockIdx.z;
     const int kb_begin = (int)(((long long)z * args.num_k_blocks) / splits);
@@ -287,37 +192,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-    return fn;
-}
-
-// bf16 row-major [rows, cols] matrix, box = box_rows x 64 columns, 128-byte swizzle
-bool encode_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
-{
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return false;
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
-    const cuuint32_t elem[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, elem,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <typename K>
 cudaError_t set_smem(K kernel, int bytes)
 {
@@ -362,7 +236,7 @@ void prn_bf16_release(mpn_handle *h)
 }
 
 int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_f32, const __nv_bfloat16 *x_bf16,
-                    const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, cudaStream_t s)
+                    const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, int skip_le, cudaStream_t s)
 {
     (void)x_bf16;
     if (n_max <= 0) return 0;
@@ -381,18 +255,19 @@ int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_
         GemmArgs a;
         a.m_dev = n_dev; a.m_host = n_host; a.num_k_blocks = nkb;
         a.out = ws.partial; a.split_stride = (size_t)n_max * Hd; a.ldo = Hd; a.bias = nullptr; a.residual = nullptr;
+        a.skip_le = skip_le;
         dim3 grid(n_tiles, m_tiles, splits);
         prof_mark(s, "prn_bf16_fc1");
         gemm_bf16_kernel<kFc1BlockN, kFc1Stages, EPI_FC1_PARTIAL, 1>
             <<<grid, kGemmThreads, SmemLayout<kFc1BlockN, kFc1Stages>::kTotal, s>>>(tm->a1, tm->b1, a);
         ++launches;
         launches += launch_fc1_reduce(ws.partial, splits, a.split_stride, w.b1, Hd, n_dev, n_host, n_max, nullptr,
-                                      ws.y1_bf16, s);
+                                      ws.y1_bf16, skip_le, s);
     }
     {   // fc2 + bias + ReLU + residual
         GemmArgs a;
         a.m_dev = n_dev; a.m_host = n_host; a.num_k_blocks = Hd / BLOCK_K;
-        a.out = logits; a.split_stride = 0; a.ldo = D; a.bias = w.b2; a.residual = x_f32;
+        a.out = logits; a.split_stride = 0; a.ldo = D; a.bias = w.b2; a.residual = x_f32; a.skip_le = skip_le;
         dim3 grid(D / kFc2BlockN, m_tiles, 1);
         prof_mark(s, "prn_bf16_fc2");
         gemm_bf16_kernel<kFc2BlockN, kFc2Stages, EPI_FC2_RESIDUAL, 2>

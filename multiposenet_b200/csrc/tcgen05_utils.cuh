@@ -1,0 +1,158 @@
+// tcgen05 / TMA / mbarrier building blocks shared by the PRN kernels (prn_tcgen05.cu, prn_fused.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpn {
+namespace tc {
+
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // streamed once: weights
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // re-read by many CTAs: activations
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
+                                            uint64_t hint)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address          bits [0, 14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset    bits [16, 30) (unused with swizzle)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset     bits [32, 46)
+    d |= (uint64_t)1 << 46;                         // descriptor version 1   bits [46, 48)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B           bits [61, 64)
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    // the "+r" operands tie every later use of r[] to the completion of the asynchronous load
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// bf16 row-major [rows, cols] matrix, box = box_rows x 64 columns, 128-byte swizzle
+inline bool encode_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, elem,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
+}  // namespace tc
+}  // namespace mpn

@@ -446,6 +446,14 @@ class Detector:
         self._check(self._lib.mpn_get_profile(self._handle, cap, names, ms, C.byref(n)))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
+    def fused_trace(self, enable=True):
+        """Development aid (mpn_debug_fused_trace): numpy uint64 [grid, 16] of per-CTA phase timestamps in ns."""
+        cap = 1024 * 16
+        buf = (C.c_uint64 * cap)()
+        g = C.c_int32(0)
+        self._check(self._lib.mpn_debug_fused_trace(self._handle, 1 if enable else 0, buf, cap, C.byref(g)))
+        return np.frombuffer(buf, dtype=np.uint64, count=g.value * 16).reshape(g.value, 16).copy()
+
     def launch_count(self):
         last, total = C.c_int64(0), C.c_int64(0)
         self._lib.mpn_launch_count(self._handle, C.byref(last), C.byref(total))

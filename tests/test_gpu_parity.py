@@ -235,7 +235,7 @@ def test_prn_fp32_within_1e4(det6, prn_weights, n):
     np.testing.assert_allclose(got, want, rtol=RTOL_FP32, atol=RTOL_FP32 * np.abs(want).max())
 
 
-@pytest.mark.parametrize("n", [1, 5, 130])
+@pytest.mark.parametrize("n", [1, 5, 130, 256, 300])
 def test_prn_bf16_tcgen05_within_1e2_and_close_to_bf16_oracle(det6, prn_weights, n):
     x = synthetic.make_crops(n, seed=31 + n)
     got = det6.prn(_cuda(x), "bf16").cpu().numpy()

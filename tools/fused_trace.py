@@ -1,0 +1,36 @@
+"""Development aid: phase timeline of the single-kernel PRN (mpn_debug_fused_trace).  python tools/fused_trace.py [N]"""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multiposenet_b200 import Detector, DetectorConfig, synthetic
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 78
+w = synthetic.make_prn_weights()
+det = Detector(w, DetectorConfig(max_batch=8, max_boxes=32, prn_mode="bf16", prn_modes_allocated=("bf16",)))
+x = torch.from_numpy(synthetic.make_crops(n)).cuda()
+flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+for _ in range(3):
+    det.prn(x, "bf16")
+det.fused_trace(True)
+names = {0: "prologue", 1: "fc1 loads issued", 2: "fc1 mma issued", 3: "fc1 acc complete", 4: "partials stored",
+         11: "w2 fc2 chunk0 in regs", 12: "w2 fc2 next loads issued", 13: "w2 fc2 chunk0 transposed", 14: "w2 fc2 chunk 0 stored",
+         15: "w2 fc2 epilogue done", 5: "barrier1 passed", 8: "y1 stored", 6: "producer past barrier2", 9: "fc2 acc complete", 10: "logits stored"}
+for rep in range(3):
+    # many launches back to back so that the SM clock is at its loaded value; the trace holds the last launch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(300):
+        if i == 100:
+            e0.record()
+        det.prn(x, "bf16")
+    e1.record(); torch.cuda.synchronize()
+    t = det.fused_trace(True).astype(np.int64)
+    t0 = t[:, 0].min()
+    print(f"--- rep {rep}: N={n}, {e0.elapsed_time(e1) * 1e3 / 200:.1f} us per call (f32->bf16 convert + fused kernel)")
+    for slot in (0, 1, 2, 3, 4, 5, 8, 6, 9, 11, 12, 13, 14, 15, 10):
+        col = t[:, slot]
+        col = col[col > 0] - t0
+        if col.size:
+            print(f"  {names[slot]:24s} min {col.min() / 1e3:7.2f}  median {np.median(col) / 1e3:7.2f}  max {col.max() / 1e3:7.2f} us  ({col.size} CTAs)")
+det.fused_trace(False)
+det.close()
