@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -329,7 +330,11 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     MPN_ALLOC(h->person_img, NP);
     MPN_ALLOC(h->person_offsets, B + 1);
     MPN_ALLOC(h->kh_ws, B * h->max_hm_pix * 17);
+    MPN_ALLOC(h->nh_ws, B * h->max_hm_pix * 17);
     MPN_ALLOC(h->minmax_ws, B * 17 * 2);
+    MPN_ALLOC(h->hm_partial, B * (size_t)((h->max_hm_pix / 64 + 1) / 2 + 1) * 17 * 2);
+    MPN_ALLOC(h->hm_counter, B);
+    cudaMemset(h->hm_counter, 0, B * sizeof(unsigned int));
     MPN_ALLOC(h->crops_f32, NPpad * D);
     MPN_ALLOC(h->logits, NPpad * D);
     MPN_ALLOC(h->b1, Hd);
@@ -355,9 +360,14 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     }
     h->prn_ws.n_max = (int)NPpad;
     cudaMemset(h->done_counter, 0, sizeof(unsigned int));
+    cudaMemset(h->cand_count, 0, B * sizeof(int));
     cudaMemset(h->person_offsets, 0, (B + 1) * sizeof(int));
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->own_event, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    h->cfg_use_graphs = getenv("MPN_NO_GRAPH") == nullptr;
     if (e != cudaSuccess) {
         fail(nullptr, MPN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
         mpn_destroy(h);
@@ -384,7 +394,7 @@ void mpn_destroy(mpn_handle *h)
     prn_bf16_release(h);
     prn_fused_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
-                    h->kh_ws, h->minmax_ws, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
+                    h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_counter, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -400,8 +410,13 @@ void mpn_destroy(mpn_handle *h)
     if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->prof_events_ready)
         for (int i = 0; i <= kMaxMarks; ++i) cudaEventDestroy(h->prof.ev[i]);
+    for (GraphEntry &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->own_event) cudaEventDestroy(h->own_event);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     delete h;
 }
 
@@ -471,7 +486,8 @@ int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int3
         return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 64 (it is for images divisible by 128)");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     return launched(h, launch_heatmaps(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
-                                       h->minmax_ws, minmax, (cudaStream_t)stream), true, "heatmaps");
+                                       h->minmax_ws, minmax, h->hm_partial, h->hm_counter, (cudaStream_t)stream), true,
+                    "heatmaps");
 }
 
 int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
@@ -538,32 +554,37 @@ int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *s
     return launched(h, launch_test_math(x, y, n, 1, (cudaStream_t)stream), true, "test sigmoid");
 }
 
-int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream)
+// Enqueues every kernel of the path.  With `fork` the two independent front halves run concurrently: candidates ->
+// sort/NMS -> person list on `s`, heatmap activation -> normalisation on the handle's auxiliary stream, joined before
+// the crops (the same code is what gets captured into a CUDA graph).
+static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, cudaStream_t s,
+                        bool fork)
 {
-    if (!h) return MPN_ERR_INVALID_ARGUMENT;
-    if (!in || !p || !out) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs/params/outputs is NULL");
-    if (!in->heatmap_logits) return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits is NULL");
-    if (!out->keypoint_scores || !out->keypoint_positions)
-        return fail(h, MPN_ERR_INVALID_ARGUMENT, "keypoint_scores/keypoint_positions is NULL");
-    if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
-    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t s = (cudaStream_t)stream;
-    ProfScope prof_scope(h, s);
+    cudaStream_t sa = fork ? h->aux_stream : s;
+    if (fork) {
+        MPN_CUDA(h, cudaEventRecord(h->ev_fork, s));
+        MPN_CUDA(h, cudaStreamWaitEvent(sa, h->ev_fork, 0));
+    }
     // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
     int rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, s, true);
     if (rc) return rc;
-    // 2. heatmap sigmoid / split / min-max                   (create_pb.py:73-76, 90, 92)
+    // 2. heatmap sigmoid / split / min-max, then normalise the whole map once   (create_pb.py:73-76, 90-94)
     const int hh = in->height / h->cfg.downsample, ww = in->width / h->cfg.downsample;
     float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
     rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
-                                     nullptr, s), false, "heatmaps");
+                                     nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
     if (rc) return rc;
-    // 3. normalise + crop_and_resize                         (create_pb.py:93-94, 106-109)
+    rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
+    if (rc) return rc;
+    if (fork) {
+        MPN_CUDA(h, cudaEventRecord(h->ev_join, sa));
+        MPN_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    }
+    // 3. crop_and_resize                                     (create_pb.py:106-109)
     const int n_max = in->batch * p->max_detections;
     const int *n_dev = h->person_offsets + in->batch;
     const bool bf16 = p->prn_mode == MPN_PRN_BF16;
-    if (bf16 && !h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
-    rc = launched(h, launch_crop(kh, h->minmax_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
+    rc = launched(h, launch_crop(h->nh_ws, nullptr, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
                                  h->cfg.crop_height, h->cfg.crop_width, h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
                   false, "crop");
     if (rc) return rc;
@@ -574,6 +595,104 @@ int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_
     return launched(h, launch_keypoint_decode(h->logits, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
                                               out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
                     "keypoint decode");
+}
+
+// A call is fully described by its pointers, shapes and parameters: the kernel sequence for one such description is
+// captured once into a CUDA graph and replayed afterwards (one driver call instead of eight launches + four event ops).
+static void make_graph_key(const mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out,
+                           GraphKey *k)
+{
+    memset(k, 0, sizeof(*k));
+    k->v[0] = (uint64_t)in->batch; k->v[1] = (uint64_t)in->height; k->v[2] = (uint64_t)in->width;
+    k->v[3] = (uint64_t)(uintptr_t)in->class_logits; k->v[4] = (uint64_t)(uintptr_t)in->encoded_boxes;
+    k->v[5] = (uint64_t)(uintptr_t)in->heatmap_logits;
+    const bool levels = !(in->class_logits && in->encoded_boxes) && in->level_class && in->level_boxes;
+    for (int i = 0; i < h->cfg.num_levels && levels; ++i) {
+        k->v[6 + i] = (uint64_t)(uintptr_t)in->level_class[i];
+        k->v[6 + kMaxLevels + i] = (uint64_t)(uintptr_t)in->level_boxes[i];
+    }
+    int o = 6 + 2 * kMaxLevels;
+    uint32_t f[2];
+    memcpy(&f[0], &p->score_threshold, 4); memcpy(&f[1], &p->iou_threshold, 4);
+    k->v[o++] = ((uint64_t)f[0] << 32) | f[1];
+    k->v[o++] = ((uint64_t)(uint32_t)p->max_detections << 32) | (uint32_t)p->prn_mode;
+    const void *ptrs[8] = {out->boxes, out->scores, out->num_boxes, out->keypoint_heatmaps, out->segmentation_masks,
+                           out->keypoint_scores, out->keypoint_positions, out->person_offsets};
+    for (int i = 0; i < 8; ++i) k->v[o++] = (uint64_t)(uintptr_t)ptrs[i];
+}
+
+static int run_graphed(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, cudaStream_t s)
+{
+    GraphKey key;
+    make_graph_key(h, in, p, out, &key);
+    GraphEntry *hit = nullptr, *victim = &h->graphs[0];
+    for (GraphEntry &e : h->graphs) {
+        if (e.exec && memcmp(&e.key, &key, sizeof(key)) == 0) { hit = &e; break; }
+        if (!e.exec) { victim = &e; }
+        else if (victim->exec && e.last_used < victim->last_used) victim = &e;
+    }
+    if (!hit) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;      // not capturable (legacy default stream): caller falls back to direct launches
+        }
+        const int64_t before = h->total_launches;
+        const int rc = enqueue_path(h, in, p, out, s, true);
+        const cudaError_t ec = cudaStreamEndCapture(s, &graph);
+        const int n_launches = (int)(h->total_launches - before);
+        h->total_launches = before;
+        if (rc != MPN_OK || ec != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != MPN_OK) return rc;
+            h->graphs_disabled = true;
+            return 1;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cudaGetLastError(); h->graphs_disabled = true; return 1; }
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);
+        victim->exec = exec; victim->key = key; victim->launches = n_launches;
+        hit = victim;
+    }
+    hit->last_used = ++h->graph_clock;
+    MPN_CUDA(h, cudaGraphLaunch(hit->exec, s));
+    h->last_launches = hit->launches;
+    h->total_launches += hit->launches;
+    return MPN_OK;
+}
+
+int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!in || !p || !out) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs/params/outputs is NULL");
+    if (!in->heatmap_logits) return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits is NULL");
+    if (!out->keypoint_scores || !out->keypoint_positions || !out->boxes || !out->scores || !out->num_boxes)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "an output pointer is NULL");
+    if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
+    int rc = check_image_size(h, in->batch, in->height, in->width);
+    if (rc) return rc;
+    rc = check_params(h, p);
+    if (rc) return rc;
+    if (p->prn_mode == MPN_PRN_BF16 && !h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
+    if (p->prn_mode == MPN_PRN_FP32 && !(h->cfg.prn_modes & 1)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the fp32 PRN");
+    const bool flat = in->class_logits != nullptr && in->encoded_boxes != nullptr;
+    const bool levels = in->level_class != nullptr && in->level_boxes != nullptr;
+    if (!flat && !levels) return fail(h, MPN_ERR_INVALID_ARGUMENT, "need class_logits+encoded_boxes or level_class+level_boxes");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->prof.on) {              // per-kernel timing: one stream, direct launches
+        ProfScope prof_scope(h, s);
+        return enqueue_path(h, in, p, out, s, false);
+    }
+    const bool capturable = s != nullptr && s != cudaStreamLegacy && h->cfg_use_graphs && !h->graphs_disabled;
+    if (capturable) {
+        rc = run_graphed(h, in, p, out, s);
+        if (rc <= 0) return rc;
+    }
+    return enqueue_path(h, in, p, out, s, s != nullptr && s != cudaStreamLegacy);
 }
 
 static int ensure_staging(mpn_handle *h)

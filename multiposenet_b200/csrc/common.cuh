@@ -80,8 +80,10 @@ inline void prof_mark(cudaStream_t s, const char *name)
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s);
 
+int heatmap_chunks_per_image(int B, int hh, int ww);
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
-                    float *minmax_out, cudaStream_t s);
+                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s);
+int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s);
 int launch_crop(const float *kh, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
                 const int *n_dev, int n_host, int n_max, int crop_h, int crop_w, float *crops_f32,
                 __nv_bfloat16 *crops_bf16, cudaStream_t s);

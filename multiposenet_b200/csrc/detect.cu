@@ -24,7 +24,7 @@ namespace mpn {
 
 namespace {
 
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 512;
 
 struct Anchor { float ymin, xmin, ymax, xmax; };
 
@@ -89,13 +89,6 @@ __global__ void anchors_kernel(const AnchorTable t, float4 *out)
     out[a] = make_float4(an.ymin, an.xmin, an.ymax, an.xmax);
 }
 
-__global__ void detect_reset_kernel(int *cand_count, unsigned int *done_counter, int B)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) cand_count[i] = 0;
-    if (i == 0) *done_counter = 0u;
-}
-
 // Concatenated [B, A] logits, 4 per thread as one 16-byte load over the flat array.
 __global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a, const int A, const long long total,
                                                               const int vec_ok)
@@ -149,83 +142,143 @@ __device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectAr
     return make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane), __ldg(p + 3 * plane));
 }
 
+// One CTA per image.
+//   1. candidate keys -> descending order (= score desc, anchor asc).  <= 1024 candidates: rank sort in shared memory
+//      (every key counts the keys above it; no barriers); more: bitonic sort, in shared memory up to 8192 keys and in the
+//      image's global scratch beyond that -- exact for any candidate count.
+//   2. greedy NMS in chunks of 512 candidates of that order:
+//        a. every thread decodes one box (4 gathered codes + the anchor rebuilt from its index) into shared memory
+//        b. ... and tests it against the boxes kept by earlier chunks
+//        c. the chunk is resolved in score order with one barrier per KEPT box (not per candidate): ballots of the live
+//           candidates -> first live one -> everybody tests itself against that box
+//      until max_detections boxes are kept or the candidates run out.  TensorFlow's NonMaxSuppressionV3 semantics:
+//      strict `IoU > thr`, kept boxes in descending score order.
+constexpr int kChunk = 512;
+constexpr int kMaskWords = kChunk / 32;
+constexpr int kRankSortCap = 1024;
+
+struct NmsSmem {
+    unsigned long long keys[kSortSmemCap];     // 64 KB: unsorted (rank sort source) or bitonic work area
+    unsigned long long sorted[kRankSortCap];   //  8 KB: rank sort destination
+    float4 box[kChunk];                        //  8 KB: decoded boxes of the current chunk
+    float4 kept_box[kMaxDetCap];               // 16 KB
+    int kept_local[kChunk];                    //  2 KB: chunk-local indices kept by step d
+    unsigned alive[2][kMaskWords];             // live-candidate ballots, double buffered
+};
+
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(smem_raw);            // [kSortSmemCap]
-    float4 *kept_box = reinterpret_cast<float4 *>(smem_raw + sizeof(unsigned long long) * kSortSmemCap);  // [max_det]
-    __shared__ int s_first[32];
-    __shared__ int s_is_last;
-
+    NmsSmem &sm = *reinterpret_cast<NmsSmem *>(smem_raw);
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = min(a.cand_count[img], a.key_cap);
     unsigned long long *gkeys = a.cand_keys + (size_t)img * a.key_cap;
-    unsigned long long *keys;
-    int npad = 1;
-    while (npad < C) npad <<= 1;
-    if (C <= kSortSmemCap) {
-        keys = skeys;
-        for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = (i < C) ? gkeys[i] : 0ULL;
+    const unsigned long long *keys;
+    __syncthreads();                                   // everyone has read the count ...
+    if (tid == 0) a.cand_count[img] = 0;               // ... re-arm it for the next call (no reset kernel)
+
+    if (C <= kRankSortCap) {
+        for (int i = tid; i < C; i += kNmsThreads) sm.keys[i] = gkeys[i];
+        __syncthreads();
+        const unsigned long long k0 = tid < C ? sm.keys[tid] : 0ULL;
+        const unsigned long long k1 = tid + kNmsThreads < C ? sm.keys[tid + kNmsThreads] : 0ULL;
+        int r0 = 0, r1 = 0;
+        for (int j = 0; j < C; ++j) {                  // keys are distinct (they carry the anchor index)
+            const unsigned long long kj = sm.keys[j];
+            r0 += kj > k0;
+            r1 += kj > k1;
+        }
+        if (tid < C) sm.sorted[r0] = k0;
+        if (tid + kNmsThreads < C) sm.sorted[r1] = k1;
+        keys = sm.sorted;
     } else {
-        keys = gkeys;
-        for (int i = C + tid; i < npad; i += kNmsThreads) gkeys[i] = 0ULL;
+        int npad = 1;
+        while (npad < C) npad <<= 1;
+        unsigned long long *work;
+        if (C <= kSortSmemCap) {
+            work = sm.keys;
+            for (int i = tid; i < npad; i += kNmsThreads) work[i] = (i < C) ? gkeys[i] : 0ULL;
+        } else {
+            work = gkeys;
+            for (int i = C + tid; i < npad; i += kNmsThreads) gkeys[i] = 0ULL;
+        }
+        __syncthreads();
+        for (int k = 2; k <= npad; k <<= 1) {          // bitonic sort, descending
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int p = tid; p < (npad >> 1); p += kNmsThreads) {
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    const int ixj = i | j;
+                    const unsigned long long x = work[i], y = work[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { work[i] = y; work[ixj] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        keys = work;
     }
     __syncthreads();
-    // bitonic sort, descending
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int p = tid; p < (npad >> 1); p += kNmsThreads) {
-                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                const int ixj = i | j;
-                const unsigned long long x = keys[i], y = keys[ixj];
-                const bool desc = (i & k) == 0;
-                if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[ixj] = x; }
-            }
-            __syncthreads();
-        }
-    }
 
     float *boxes_out = a.boxes + (size_t)img * a.max_det * 4;
     float *scores_out = a.scores + (size_t)img * a.max_det;
     int kept = 0;
-    for (int base = 0; base < C && kept < a.max_det; base += kNmsThreads) {
-        const int i = base + tid;
-        bool alive = i < C;
+    for (int base = 0; base < C && kept < a.max_det; base += kChunk) {
+        const int n = min(kChunk, C - base);
+        // ---- a, b: decode, test against the boxes kept so far
+        bool alive = tid < n;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         float score = 0.f;
         int anchor = -1;
         if (alive) {
-            const unsigned long long key = keys[i];
+            const unsigned long long key = keys[base + tid];
             score = __uint_as_float((unsigned)(key >> 32));
             anchor = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
             int l, loc, k;
             const Anchor an = anchor_from_index(t, anchor, &l, &loc, &k);
             box = decode_box(an, load_code(t, a, img, anchor, l, loc, k), t.sf);
-            for (int j = kept - 1; j >= 0; --j)
-                if (nms_iou(box, kept_box[j]) > a.iou_thr) { alive = false; break; }
+            sm.box[tid] = box;
+            for (int j = 0; j < kept; ++j)
+                if (nms_iou(box, sm.kept_box[j]) > a.iou_thr) { alive = false; break; }
         }
-        // resolve the chunk in score order: the first live candidate is kept, then suppresses the rest
-        while (kept < a.max_det) {
-            const unsigned m = __ballot_sync(0xffffffffu, alive);
-            if (lane == 0) s_first[warp] = m ? (warp * 32 + __ffs(m) - 1) : 0x7fffffff;
+        __syncthreads();                               // sm.box complete
+        // ---- c: resolve the chunk in score order, ONE barrier per kept box: every warp publishes its ballot of live
+        //      candidates (double buffered), every thread finds the first live candidate from the 16 words, reads that
+        //      candidate's box from sm.box and drops itself if it overlaps it too much; the winner records itself.
+        int nk = 0;
+        const int room = a.max_det - kept;
+        unsigned my_word = __ballot_sync(0xffffffffu, alive);
+        for (int iter = 0; nk < room; ++iter) {
+            unsigned *pub = sm.alive[iter & 1];
+            if (lane == 0) pub[warp] = my_word;
             __syncthreads();
-            int first = s_first[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            if (first == 0x7fffffff) break;     // uniform: every thread reads the same s_first
+            const unsigned wv = lane < kMaskWords ? pub[lane] : 0u;
+            const unsigned nz = __ballot_sync(0xffffffffu, wv != 0u);
+            if (nz == 0u) break;                       // uniform over the CTA: nothing left alive in this chunk
+            const int fw = __ffs(nz) - 1;
+            const int first = (fw << 5) + __ffs(__shfl_sync(0xffffffffu, wv, fw)) - 1;
             if (tid == first) {
-                kept_box[kept] = box;
-                reinterpret_cast<float4 *>(boxes_out)[kept] = box;
-                scores_out[kept] = score;
-                if (a.sel_anchor) a.sel_anchor[(size_t)img * a.max_det + kept] = anchor;
+                sm.kept_local[nk] = first;
+                alive = false;
+            } else if (alive && nms_iou(box, sm.box[first]) > a.iou_thr) {
                 alive = false;
             }
-            __syncthreads();
-            const float4 kb = kept_box[kept];
-            ++kept;
-            if (alive && nms_iou(box, kb) > a.iou_thr) alive = false;
+            ++nk;
+            my_word = __ballot_sync(0xffffffffu, alive);
         }
-        __syncthreads();   // s_first / kept_box stable before the next chunk
+        __syncthreads();                               // sm.kept_local complete
+        // ---- e: the kept candidates write themselves out
+        for (int k = tid; k < nk; k += kNmsThreads) {
+            const int i = sm.kept_local[k];
+            const float4 bx = sm.box[i];
+            const unsigned long long key = keys[base + i];
+            sm.kept_box[kept + k] = bx;
+            reinterpret_cast<float4 *>(boxes_out)[kept + k] = bx;
+            scores_out[kept + k] = __uint_as_float((unsigned)(key >> 32));
+            if (a.sel_anchor)
+                a.sel_anchor[(size_t)img * a.max_det + kept + k] = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        }
+        kept += nk;
+        __syncthreads();
     }
     // zero padding (detector/utils/nms.py:47-52)
     for (int k = kept + tid; k < a.max_det; k += kNmsThreads) {
@@ -237,21 +290,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
         a.num_boxes[img] = kept;
         if (a.n_candidates) a.n_candidates[img] = C;
     }
-    // ---- last CTA: flat person list in image order (create_pb.py:96-103) ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned done = atomicAdd(a.done_counter, 1u);
-        s_is_last = (done == (unsigned)a.B - 1u);
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    if (warp == 0) {
+}
+
+// Flat person list in image order (create_pb.py:96-103): person_offsets = exclusive scan of num_boxes, and for every
+// person row its box and image.  One small CTA; runs after sort_nms_kernel.
+__global__ void __launch_bounds__(256) person_list_kernel(const DetectArgs a)
+{
+    __shared__ int s_off[1025];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
         int running = 0;
         for (int b0 = 0; b0 < a.B; b0 += 32) {
             const int b = b0 + lane;
-            const int n = (b < a.B) ? __ldcg(a.num_boxes + b) : 0;
+            const int n = (b < a.B) ? a.num_boxes[b] : 0;
             int incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -259,23 +310,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
                 if (lane >= o) incl += v;
             }
             if (b < a.B) {
-                a.person_offsets[b] = running + incl - n;
-                if (a.person_offsets_out) a.person_offsets_out[b] = running + incl - n;
+                const int off = running + incl - n;
+                if (b < 1024) s_off[b] = off;
+                a.person_offsets[b] = off;
+                if (a.person_offsets_out) a.person_offsets_out[b] = off;
             }
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) {
             a.person_offsets[a.B] = running;
             if (a.person_offsets_out) a.person_offsets_out[a.B] = running;
-            *a.done_counter = 0u;
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < a.B * a.max_det; idx += kNmsThreads) {
+    for (int idx = tid; idx < a.B * a.max_det; idx += blockDim.x) {
         const int b = idx / a.max_det, k = idx - b * a.max_det;
-        if (k < __ldcg(a.num_boxes + b)) {
-            const int row = a.person_offsets[b] + k;
-            reinterpret_cast<float4 *>(a.person_box)[row] = __ldcg(reinterpret_cast<const float4 *>(a.boxes) + idx);
+        if (k < a.num_boxes[b]) {
+            const int row = (b < 1024 ? s_off[b] : a.person_offsets[b]) + k;
+            reinterpret_cast<float4 *>(a.person_box)[row] = reinterpret_cast<const float4 *>(a.boxes)[idx];
             a.person_img[row] = b;
         }
     }
@@ -292,17 +344,12 @@ int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
 {
     static bool attr_set = false;
-    const size_t smem = sizeof(unsigned long long) * kSortSmemCap + sizeof(float4) * (size_t)a.max_det;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(unsigned long long) * kSortSmemCap + sizeof(float4) * kMaxDetCap));
+        cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
         if (e != cudaSuccess) return -(int)e;
         attr_set = true;
     }
     int launches = 0;
-    prof_mark(s, "detect_reset");
-    detect_reset_kernel<<<(a.B + 255) / 256, 256, 0, s>>>(a.cand_count, a.done_counter, a.B);
-    ++launches;
     if (a.cls) {
         const long long total = (long long)a.B * t.num_anchors;
         const long long threads = (total + 3) / 4;
@@ -316,8 +363,13 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
     }
     ++launches;
     prof_mark(s, "sort_nms");
-    sort_nms_kernel<<<a.B, kNmsThreads, smem, s>>>(t, a);
+    sort_nms_kernel<<<a.B, kNmsThreads, sizeof(NmsSmem), s>>>(t, a);
     ++launches;
+    if (a.person_box) {
+        prof_mark(s, "person_list");
+        person_list_kernel<<<1, 256, 0, s>>>(a);
+        ++launches;
+    }
     return launches;
 }
 

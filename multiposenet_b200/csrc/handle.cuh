@@ -13,13 +13,28 @@ struct HostSlot {
 };
 }  // namespace mpn
 
+namespace mpn {
+constexpr int kGraphCache = 24;
+struct GraphKey { uint64_t v[6 + 2 * kMaxLevels + 2 + 8]; };
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    int launches;
+    uint64_t last_used;
+};
+}  // namespace mpn
+
 struct mpn_handle {
     mpn_config cfg;
     int D;                  // crop_h * crop_w * num_keypoints
     int max_anchors, key_cap, max_hm_pix, max_persons;
     char err[512];
-    cudaStream_t own_stream;
-    cudaEvent_t own_event;
+    cudaStream_t own_stream, aux_stream;
+    cudaEvent_t own_event, ev_fork, ev_join;
+    // CUDA graphs of mpn_run, keyed by the call's pointers / shapes / parameters
+    mpn::GraphEntry graphs[mpn::kGraphCache];
+    uint64_t graph_clock;
+    bool cfg_use_graphs, graphs_disabled;
     // detect workspace
     unsigned long long *cand_keys;
     int *cand_count;
@@ -29,7 +44,10 @@ struct mpn_handle {
     int *person_offsets;
     // heatmap workspace
     float *kh_ws;
+    float *nh_ws;           // normalised heatmaps (create_pb.py:93-94), never returned
     float *minmax_ws;
+    int *hm_partial;        // [B, chunks, 17, 2] per-CTA (min, max) of the heatmap kernel
+    unsigned int *hm_counter;   // [B] CTAs finished per image (self re-arming)
     // PRN workspace / weights
     float *crops_f32, *logits;
     __nv_bfloat16 *crops_bf16;

@@ -25,81 +25,94 @@ constexpr int kCH = 18;             // channels of the subnet output
 constexpr int kHmThreads = 288;     // 9 warps: 288 float4 = 64 pixels x 18 channels
 constexpr int kHmPix = 64;
 
-__global__ void heatmap_reset_kernel(int *minmax, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) minmax[i] = (i & 1) ? 0 : 0x7f800000;   // (min, max) pairs: +inf, 0  (sigmoid output is >= 0)
-}
-
+// grid = (chunks per image, B).  Thread t of a CTA always sees the four channels (4 t + j) mod 18 of its 64-pixel tiles,
+// so its running min / max live in registers.  Outputs are written straight from registers: within a warp the 17-channel
+// rows are one contiguous run of addresses, so the scalar stores coalesce into full lines without a shared-memory
+// repack or any barrier in the streaming loop.  Per-CTA (min, max) go to a small partial array; the last CTA of each
+// image (threadfence + counter) folds them into minmax[b] and re-arms the counter, so no reset kernel is needed.
 __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__restrict__ hml, const int npix,
                                                              const int tiles_per_img, float *__restrict__ kh,
-                                                             float *__restrict__ seg, int *__restrict__ minmax)
+                                                             float *__restrict__ seg, int *__restrict__ partial,
+                                                             unsigned int *__restrict__ counter,
+                                                             int *__restrict__ minmax)
 {
-    __shared__ __align__(16) float s_val[kHmThreads * 4];
     __shared__ int s_min[kNK], s_max[kNK];
+    __shared__ int s_last;
     const int img = blockIdx.y, tid = threadIdx.x;
+    int ooff[4];          // output element offset inside the tile: kh index (pixel*17 + c), or -(pixel + 1) for the mask
     int ch[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ch[j] = (4 * tid + j) % kCH;
+    for (int j = 0; j < 4; ++j) {
+        const int e = 4 * tid + j, p = e / kCH;
+        ch[j] = e - p * kCH;
+        ooff[j] = ch[j] < kNK ? p * kNK + ch[j] : -(p + 1);
+    }
     float mn[4], mx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { mn[j] = __int_as_float(0x7f800000); mx[j] = 0.0f; }
     if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
 
-    for (int tile = blockIdx.x; tile < tiles_per_img; tile += gridDim.x) {
-        const int pix0 = tile * kHmPix;
-        const int npx = min(kHmPix, npix - pix0);
-        const size_t gpix = (size_t)img * npix + pix0;
-        float v[4];
-        if (4 * tid + 3 < npx * kCH) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(hml + gpix * kCH) + tid);
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
+    float *kh_img = kh + (size_t)img * npix * kNK;
+    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
+    // npix is a multiple of 64 on this path (images are multiples of 128): every tile is full.  Two tiles per trip.
+    for (int tile = blockIdx.x; tile < tiles_per_img; tile += 2 * gridDim.x) {
+        const int tile2 = tile + gridDim.x;
+        const bool two = tile2 < tiles_per_img;
+        const float4 qa = __ldcs(src + (size_t)tile * kHmThreads + tid);
+        const float4 qb = two ? __ldcs(src + (size_t)tile2 * kHmThreads + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (ch[j] < kNK) {
-                    v[j] = exact_sigmoidf(v[j]);
-                    mn[j] = fminf(mn[j], v[j]);
-                    mx[j] = fmaxf(mx[j], v[j]);
+        for (int j = 0; j < 4; ++j) {
+            if (ch[j] < kNK) {
+                va[j] = exact_sigmoidf(va[j]);
+                mn[j] = fminf(mn[j], va[j]); mx[j] = fmaxf(mx[j], va[j]);
+                kh_img[(size_t)tile * kHmPix * kNK + ooff[j]] = va[j];
+                if (two) {
+                    vb[j] = exact_sigmoidf(vb[j]);
+                    mn[j] = fminf(mn[j], vb[j]); mx[j] = fmaxf(mx[j], vb[j]);
+                    kh_img[(size_t)tile2 * kHmPix * kNK + ooff[j]] = vb[j];
                 }
-            }
-            *reinterpret_cast<float4 *>(s_val + 4 * tid) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        __syncthreads();
-        if (tid < (kHmPix * kNK) / 4) {
-            if (4 * tid + 3 < npx * kNK) {
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = 4 * tid + j;
-                    const int p = e / kNK, c = e - p * kNK;
-                    o[j] = s_val[p * kCH + c];
-                }
-                reinterpret_cast<float4 *>(kh + gpix * kNK)[tid] = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        } else if (seg != nullptr) {
-            const int t2 = tid - (kHmPix * kNK) / 4;
-            if (4 * t2 + 3 < npx) {
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = s_val[(4 * t2 + j) * kCH + kNK];
-                reinterpret_cast<float4 *>(seg + gpix)[t2] = make_float4(o[0], o[1], o[2], o[3]);
+            } else if (seg_img) {
+                seg_img[(size_t)tile * kHmPix - ooff[j] - 1] = va[j];
+                if (two) seg_img[(size_t)tile2 * kHmPix - ooff[j] - 1] = vb[j];
             }
         }
-        __syncthreads();
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (ch[j] < kNK) {
-            atomicMin(&s_min[ch[j]], __float_as_int(mn[j]));
+            atomicMin(&s_min[ch[j]], __float_as_int(mn[j]));     // sigmoid output is >= 0: integer order == float order
             atomicMax(&s_max[ch[j]], __float_as_int(mx[j]));
         }
     }
     __syncthreads();
-    if (tid < kNK) {
-        atomicMin(minmax + ((size_t)img * kNK + tid) * 2 + 0, s_min[tid]);
-        atomicMax(minmax + ((size_t)img * kNK + tid) * 2 + 1, s_max[tid]);
+    int *my = partial + ((size_t)img * gridDim.x + blockIdx.x) * kNK * 2;
+    if (tid < kNK) { my[tid * 2] = s_min[tid]; my[tid * 2 + 1] = s_max[tid]; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counter + img, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
+    __syncthreads();
+    if (tid < kNK * 16) {
+        const int c = tid % kNK, slice = tid / kNK;
+        int lo = 0x7f800000, hi = 0;
+        for (int i = slice; i < (int)gridDim.x; i += 16) {
+            const int *q = partial + ((size_t)img * gridDim.x + i) * kNK * 2 + c * 2;
+            lo = min(lo, __ldcg(q)); hi = max(hi, __ldcg(q + 1));
+        }
+        atomicMin(&s_min[c], lo); atomicMax(&s_max[c], hi);
     }
+    __syncthreads();
+    if (tid < kNK) {
+        minmax[((size_t)img * kNK + tid) * 2] = s_min[tid];
+        minmax[((size_t)img * kNK + tid) * 2 + 1] = s_max[tid];
+    }
+    if (tid == 0) counter[img] = 0u;
 }
 
 // create_pb.py:93-94 on one tap
@@ -108,59 +121,138 @@ __device__ __forceinline__ float normalise_tap(float v, float m, float M, float 
     return fmul(fdiv(fsub(v, m), fsub(M, m)), mask);
 }
 
-// One thread per output sample (n, cy, cx, c); j = (cy*crop_w + cx)*17 + c is also the PRN input column
-// (detector/prn.py:17).  Sampling grid and lerp order of TF 1.15 CropAndResize (crop_and_resize_op.cc).
-__global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
+// create_pb.py:93-94 over the whole map: nh = (kh - m) / (M - m) * float(M > 0.2), float4 at a time.  Normalising every
+// heatmap pixel once costs one division per pixel; normalising the four taps of every crop sample costs 4 N D divisions,
+// which is 3x (config 2) to 30x (crowded scenes) more.  grid = (chunks, B), every CTA stays inside one image.
+__global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
+                                                        const int n4_per_img, float *__restrict__ nh)
+{
+    __shared__ float s_m[kNK], s_d[kNK], s_mask[kNK];
+    const int img = blockIdx.y;
+    if (threadIdx.x < kNK) {
+        const float m = __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2);
+        const float M = __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2 + 1);
+        s_m[threadIdx.x] = m;
+        s_d[threadIdx.x] = fsub(M, m);
+        s_mask[threadIdx.x] = (M > 0.2f) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    const float4 *src = reinterpret_cast<const float4 *>(kh) + (size_t)img * n4_per_img;
+    float4 *dst = reinterpret_cast<float4 *>(nh) + (size_t)img * n4_per_img;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_img; i += gridDim.x * blockDim.x) {
+        const float4 v = __ldcg(src + i);
+        int c = (int)((4u * (unsigned)i) % (unsigned)kNK);
+        float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = fmul(fdiv(fsub(o[k], s_m[c]), s_d[c]), s_mask[c]);
+            c = (c + 1 == kNK) ? 0 : c + 1;
+        }
+        dst[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// tf.image.crop_and_resize (create_pb.py:106-109; TF 1.15 crop_and_resize_op.cc: bilinear, extrapolation 0) of one
+// person per blockIdx.x, a band of crop rows per blockIdx.y.  The sampling geometry of every crop pixel (tap offsets and
+// lerp weights, in the op's own fp32 operation order) is computed once into shared memory; the main loop then walks the
+// output in memory order, four consecutive samples j = (cy*crop_w + cx)*17 + c per thread (j is also the PRN input
+// column, detector/prn.py:17), so that the fp32 and bf16 rows are written as 16- and 8-byte vectors.
+struct PixTab {
+    int top, bot;        // element offsets of the two source rows (row * ww * 17)
+    int left, right;     // element offsets of the two source columns (col * 17)
+    float ly, lx;
+    int valid;
+};
+constexpr int kCropBands = 4;
+constexpr int kCropMaxPix = 1024;     // pixels of one band held in shared memory
+
+__global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src, const float *__restrict__ minmax,
                                                    const int hh, const int ww, const float *__restrict__ boxes,
                                                    const int *__restrict__ box_ind, const int *__restrict__ n_dev,
                                                    const int n_host, const int crop_h, const int crop_w,
                                                    float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
 {
+    __shared__ PixTab s_tab[kCropMaxPix];
+    __shared__ float s_m[kNK], s_M[kNK], s_mask[kNK];
     const int n = blockIdx.x;
     const int N = n_dev ? *n_dev : n_host;
     if (n >= N) return;
-    const int D = crop_h * crop_w * kNK;
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= D) return;
-    const int pos = j / kNK, c = j - pos * kNK;
-    const int cy = pos / crop_w, cx = pos - cy * crop_w;
+    const int rows_per_band = (crop_h + gridDim.y - 1) / gridDim.y;
+    const int cy0 = blockIdx.y * rows_per_band, cy1 = min(crop_h, cy0 + rows_per_band);
+    if (cy0 >= cy1) return;
+    const int npix = (cy1 - cy0) * crop_w;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
     const int b = __ldg(box_ind + n);
     const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
     const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
-    float in_y, in_x;
-    if (crop_h > 1) {
-        const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(crop_h - 1));
-        in_y = fadd(fmul(y1, hm1), fmul((float)cy, hs));
-    } else {
-        in_y = fmul(fmul(0.5f, fadd(y1, y2)), hm1);
+    if (minmax != nullptr && threadIdx.x < kNK) {
+        const float m = __ldg(minmax + ((size_t)b * kNK + threadIdx.x) * 2);
+        const float M = __ldg(minmax + ((size_t)b * kNK + threadIdx.x) * 2 + 1);
+        s_m[threadIdx.x] = m; s_M[threadIdx.x] = M; s_mask[threadIdx.x] = (M > 0.2f) ? 1.0f : 0.0f;
     }
-    if (crop_w > 1) {
-        const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(crop_w - 1));
-        in_x = fadd(fmul(x1, wm1), fmul((float)cx, ws));
-    } else {
-        in_x = fmul(fmul(0.5f, fadd(x1, x2)), wm1);
-    }
-    float r = 0.0f;
-    if (!(in_y < 0.0f || in_y > hm1 || in_x < 0.0f || in_x > wm1)) {
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const int cy = cy0 + p / crop_w, cx = p % crop_w;
+        float in_y, in_x;
+        if (crop_h > 1) {
+            const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(crop_h - 1));
+            in_y = fadd(fmul(y1, hm1), fmul((float)cy, hs));
+        } else {
+            in_y = fmul(fmul(0.5f, fadd(y1, y2)), hm1);
+        }
+        if (crop_w > 1) {
+            const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(crop_w - 1));
+            in_x = fadd(fmul(x1, wm1), fmul((float)cx, ws));
+        } else {
+            in_x = fmul(fmul(0.5f, fadd(x1, x2)), wm1);
+        }
+        PixTab t;
+        t.valid = !(in_y < 0.0f || in_y > hm1 || in_x < 0.0f || in_x > wm1);
         const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
         const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
-        const float ly = fsub(in_y, (float)top), lx = fsub(in_x, (float)left);
-        const float *img = kh + (size_t)b * hh * ww * kNK + c;
-        float tl = __ldg(img + ((size_t)top * ww + left) * kNK), tr = __ldg(img + ((size_t)top * ww + right) * kNK);
-        float bl = __ldg(img + ((size_t)bot * ww + left) * kNK), br = __ldg(img + ((size_t)bot * ww + right) * kNK);
-        if (minmax != nullptr) {
-            const float m = __ldg(minmax + ((size_t)b * kNK + c) * 2), M = __ldg(minmax + ((size_t)b * kNK + c) * 2 + 1);
-            const float mask = (M > 0.2f) ? 1.0f : 0.0f;
-            tl = normalise_tap(tl, m, M, mask); tr = normalise_tap(tr, m, M, mask);
-            bl = normalise_tap(bl, m, M, mask); br = normalise_tap(br, m, M, mask);
-        }
-        const float t = fadd(tl, fmul(fsub(tr, tl), lx));
-        const float bt = fadd(bl, fmul(fsub(br, bl), lx));
-        r = fadd(t, fmul(fsub(bt, t), ly));
+        t.top = t.valid ? top * ww * kNK : 0; t.bot = t.valid ? bot * ww * kNK : 0;
+        t.left = t.valid ? left * kNK : 0; t.right = t.valid ? right * kNK : 0;
+        t.ly = fsub(in_y, (float)top); t.lx = fsub(in_x, (float)left);
+        s_tab[p] = t;
     }
-    if (out_f32) out_f32[(size_t)n * D + j] = r;
-    if (out_bf16) out_bf16[(size_t)n * D + j] = __float2bfloat16_rn(r);
+    __syncthreads();
+    const float *img = src + (size_t)b * hh * ww * kNK;
+    const int D = crop_h * crop_w * kNK;
+    const int j_begin = cy0 * crop_w * kNK, n4 = npix * kNK / 4;     // crop_w * 17 * rows is a multiple of 4 for 36 columns
+    const bool norm = minmax != nullptr;
+    for (int f = threadIdx.x; f < n4; f += blockDim.x) {
+        const int jl = 4 * f;
+        int p = jl / kNK, c = jl - p * kNK;
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const PixTab t = s_tab[p];
+            float v = 0.0f;
+            if (t.valid) {
+                const float *q = img + c;
+                float tl = __ldg(q + t.top + t.left), tr = __ldg(q + t.top + t.right);
+                float bl = __ldg(q + t.bot + t.left), br = __ldg(q + t.bot + t.right);
+                if (norm) {
+                    const float m = s_m[c], M = s_M[c], mask = s_mask[c];
+                    tl = normalise_tap(tl, m, M, mask); tr = normalise_tap(tr, m, M, mask);
+                    bl = normalise_tap(bl, m, M, mask); br = normalise_tap(br, m, M, mask);
+                }
+                const float tp = fadd(tl, fmul(fsub(tr, tl), t.lx));
+                const float bt = fadd(bl, fmul(fsub(br, bl), t.lx));
+                v = fadd(tp, fmul(fsub(bt, tp), t.ly));
+            }
+            r[k] = v;
+            if (++c == kNK) { c = 0; ++p; }
+        }
+        const size_t o = (size_t)n * D + j_begin + jl;
+        if (out_f32) *reinterpret_cast<float4 *>(out_f32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+        if (out_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<const unsigned *>(&lo);
+            u.y = *reinterpret_cast<const unsigned *>(&hi);
+            *reinterpret_cast<uint2 *>(out_bf16 + o) = u;
+        }
+    }
 }
 
 // inference/utils.py:29-52.  One CTA of 17 x 32 threads: thread (c, q) scans positions q, q+32, ...
@@ -209,39 +301,59 @@ __global__ void minmax_copy_kernel(const float *ws, float *out, int n)
 
 }  // namespace
 
+int heatmap_chunks_per_image(int B, int hh, int ww)
+{
+    // two 64-pixel tiles per CTA, one trip: every load of the kernel is issued in the first few hundred cycles of a
+    // CTA's life and the many resident CTAs per SM hide the HBM latency and the sigmoid dependency chains
+    (void)B;
+    const int tiles = (hh * ww + kHmPix - 1) / kHmPix;
+    return (tiles + 1) / 2;
+}
+
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
-                    float *minmax_out, cudaStream_t s)
+                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s)
 {
     const int npix = hh * ww;
     const int tiles = (npix + kHmPix - 1) / kHmPix;
-    int per_img = (148 * 7 + B - 1) / B;
-    if (per_img > tiles) per_img = tiles;
-    if (per_img < 1) per_img = 1;
     int launches = 0;
-    const int nmm = B * kNK * 2;
-    prof_mark(s, "heatmap_reset");
-    heatmap_reset_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(reinterpret_cast<int *>(minmax_ws), nmm);
-    ++launches;
-    dim3 grid(per_img, B);
+    dim3 grid(heatmap_chunks_per_image(B, hh, ww), B);
     prof_mark(s, "heatmap");
-    heatmap_kernel<<<grid, kHmThreads, 0, s>>>(hml, npix, tiles, kh, seg, reinterpret_cast<int *>(minmax_ws));
+    heatmap_kernel<<<grid, kHmThreads, 0, s>>>(hml, npix, tiles, kh, seg, partial_ws, counter_ws,
+                                               reinterpret_cast<int *>(minmax_ws));
     ++launches;
     if (minmax_out) {
+        const int nmm = B * kNK * 2;
         minmax_copy_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(minmax_ws, minmax_out, nmm);
         ++launches;
     }
     return launches;
 }
 
-int launch_crop(const float *kh, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
+int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s)
+{
+    const int n4 = hh * ww * kNK / 4;        // hh * ww is a multiple of 64 on this path
+    int per_img = (148 * 8 + B - 1) / B;
+    const int max_blocks = (n4 + 255) / 256;
+    if (per_img > max_blocks) per_img = max_blocks;
+    prof_mark(s, "normalise");
+    normalise_kernel<<<dim3(per_img, B), 256, 0, s>>>(kh, minmax, n4, nh);
+    return 1;
+}
+
+int launch_crop(const float *src, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
                 const int *n_dev, int n_host, int n_max, int crop_h, int crop_w, float *crops_f32,
                 __nv_bfloat16 *crops_bf16, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
-    const int D = crop_h * crop_w * kNK;
-    dim3 grid(n_max, (D + 255) / 256);
+    int bands = kCropBands;
+    while (((crop_h + bands - 1) / bands) * crop_w > kCropMaxPix) ++bands;
+    // every band must start at a multiple of 4 samples: rows_per_band * crop_w * 17 % 4 == 0
+    while (bands > 1 && ((((crop_h + bands - 1) / bands) * crop_w * kNK) % 4 != 0)) --bands;
+    if (((crop_h + bands - 1) / bands) * crop_w > kCropMaxPix || (crop_h * crop_w * kNK) % 4 != 0)
+        return -(int)cudaErrorInvalidValue;
+    dim3 grid(n_max, bands);
     prof_mark(s, "crop");
-    crop_kernel<<<grid, 256, 0, s>>>(kh, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32,
+    crop_kernel<<<grid, 256, 0, s>>>(src, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32,
                                      crops_bf16);
     return 1;
 }

@@ -383,6 +383,32 @@ def test_host_pipeline_pinned_inputs_three_in_flight(det6, prn_weights):
     assert not all(np.array_equal(ref[0]["boxes"], r["boxes"]) for r in ref[1:])
 
 
+def test_graph_replay_on_a_side_stream_equals_direct_launches(det6, prn_weights):
+    """On a non-default stream mpn_run captures the kernel sequence (forked front halves included) into a CUDA graph
+    and replays it; the results must be the bits of the direct launches on the default stream."""
+    wl = synthetic.WORKLOADS["tiny"]
+    sets = [synthetic.make_inputs(wl, replicate=r) for r in range(2)]
+    dev = [{k: _cuda(s[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")} for s in sets]
+    direct = []
+    for d in dev:
+        out = det6.run_device(d["encoded_boxes"], d["class_logits"], d["heatmap_logits"], prn_mode="bf16")
+        torch.cuda.synchronize()
+        direct.append({k: v.cpu().numpy().copy() for k, v in out.items()})
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(3):                        # first pass captures, later passes replay
+        for d, want in zip(dev, direct):
+            with torch.cuda.stream(side):
+                out = det6.run_device(d["encoded_boxes"], d["class_logits"], d["heatmap_logits"], prn_mode="bf16")
+            side.synchronize()
+            n = int(want["person_offsets"][-1])
+            for k, v in out.items():
+                rows = n if k in ("keypoint_scores", "keypoint_positions") else None
+                assert_bit_equal(v.cpu().numpy()[:rows], want[k][:rows], f"{k} (pass {rep})")
+    last, _ = det6.launch_count()
+    assert last >= 7
+
+
 def test_detector_call_keeps_the_reference_output_contract(det6, prn_weights):
     """inference/detector.py:36-61 for one image: batch dimension stripped, rows filtered by score > threshold,
     num_boxes left unfiltered."""
