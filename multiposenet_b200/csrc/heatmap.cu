@@ -163,7 +163,7 @@ struct PixTab {
     float ly, lx;
     int valid;
 };
-constexpr int kCropBands = 4;
+constexpr int kCropBands = 14;   // 4 crop rows per CTA: enough CTAs in flight to hide the tap-gather latency
 constexpr int kCropMaxPix = 1024;     // pixels of one band held in shared memory
 
 __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src, const float *__restrict__ minmax,

@@ -4,9 +4,10 @@
 // (tf.nn.softmax(axis=1): p = exp(l - max) * (1 / sum)), keypoint_scores = max p, keypoint_positions =
 // (argmax // 36 / 56, argmax % 36 / 36) with tf.argmax's first-index tie rule.
 //
-// One CTA of 17 x 32 threads per person; thread (c, q) owns positions q, q+32, ... of channel c, so the CTA reads the
-// person's 137 KB logit row exactly once, fully coalesced (flat index = thread + 544 * i), and keeps its 63 values in
-// registers for the second pass.  Softmax probabilities are never written.
+// One thread-block CLUSTER of 4 CTAs per person, each CTA of 17 x 32 threads owning a quarter of the 2016 positions
+// (a contiguous 34 KB slab of the person's logit row, read exactly once, fully coalesced; 16 values per thread stay in
+// registers for the second pass).  The per-channel maxima, exp-sums and first-argmax candidates of the four CTAs are
+// combined through distributed shared memory (two cluster barriers); softmax probabilities are never written.
 //
 // argmax rule, bit-matched to the oracle without depending on the summation order of the denominator:
 // p[i] = e[i] * r with r = 1/sum and e[i] = exp(l[i] - lmax) <= 1.  e[i] * r == r iff e[i] == 1.0f (for e[i] <= 1 - 2^-24
@@ -22,30 +23,56 @@ namespace {
 constexpr int kNK = 17;
 constexpr int kLanes = 32;
 constexpr int kThreads = kNK * kLanes;   // 544
-constexpr int kMaxPerThread = 64;        // positions per thread held in registers (56*36/32 = 63)
+constexpr int kCluster = 4;
+constexpr int kMaxPerThread = 16;        // positions per thread: ceil(2048 / 4 / 32)
 
-__global__ void __launch_bounds__(kThreads) keypoint_decode_kernel(const float *__restrict__ logits,
-                                                                   const int *__restrict__ n_dev, const int n_host,
-                                                                   const int crop_h, const int crop_w,
-                                                                   float *__restrict__ scores,
-                                                                   float *__restrict__ positions,
-                                                                   int *__restrict__ argmax_out)
+__device__ __forceinline__ unsigned cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ const T *peer_shared(const T *p, unsigned rank)
+{
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(p)), "r"(rank));
+    return reinterpret_cast<const T *>(out);
+}
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__ n_dev, const int n_host, const int crop_h,
+                       const int crop_w, float *__restrict__ scores, float *__restrict__ positions,
+                       int *__restrict__ argmax_out)
 {
     __shared__ float s_f[kNK][kLanes + 1];
     __shared__ int s_i[kNK][kLanes + 1];
-    __shared__ float s_max[kNK];
-    const int n = blockIdx.x;
+    __shared__ float s_max[kNK];          // this CTA's per-channel maximum (read by the peers)
+    __shared__ float s_sum[kNK];          // this CTA's per-channel sum of exp(l - global max)
+    __shared__ int s_first[kNK];          // this CTA's first position with exp(l - global max) == 1
+    __shared__ float s_gmax[kNK];
+    const int n = blockIdx.x / kCluster;
+    const unsigned rank = cluster_rank();
     const int N = n_dev ? *n_dev : n_host;
-    if (n >= N) return;
+    if (n >= N) return;                   // uniform over the cluster
     const int P = crop_h * crop_w;
+    const int per = (P + kCluster - 1) / kCluster;
+    const int p0 = (int)rank * per, p1 = min(P, p0 + per);
     const int tid = threadIdx.x, c = tid % kNK, q = tid / kNK;
-    const float *row = logits + (size_t)n * P * kNK;
+    const float *row = logits + (size_t)n * P * kNK + (size_t)p0 * kNK;
     float v[kMaxPerThread];
     float lmax = -__int_as_float(0x7f800000);
 #pragma unroll
     for (int i = 0; i < kMaxPerThread; ++i) {
-        const int p = q + kLanes * i;
-        v[i] = (p < P) ? __ldg(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
+        const int p = p0 + q + kLanes * i;
+        v[i] = (p < p1) ? __ldcs(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
         lmax = fmaxf(lmax, v[i]);
     }
     s_f[c][q] = lmax;
@@ -55,33 +82,49 @@ __global__ void __launch_bounds__(kThreads) keypoint_decode_kernel(const float *
         for (int i = 1; i < kLanes; ++i) m = fmaxf(m, s_f[tid][i]);
         s_max[tid] = m;
     }
+    cluster_sync_all();                   // every CTA's s_max is visible cluster-wide
+    if (tid < kNK) {
+        float m = s_max[tid];
+        for (unsigned r = 0; r < kCluster; ++r)
+            if (r != rank) m = fmaxf(m, *peer_shared(&s_max[tid], r));
+        s_gmax[tid] = m;
+    }
     __syncthreads();
-    lmax = s_max[c];
+    lmax = s_gmax[c];
     float sum = 0.0f;
     int first = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < kMaxPerThread; ++i) {
-        const int p = q + kLanes * i;
-        if (p < P) {
+        const int p = p0 + q + kLanes * i;
+        if (p < p1) {
             const float e = exact_expf(fsub(v[i], lmax));
             sum = fadd(sum, e);
             if (e == 1.0f && p < first) first = p;
         }
     }
-    __syncthreads();
     s_f[c][q] = sum; s_i[c][q] = first;
     __syncthreads();
     if (tid < kNK) {
         float S = 0.0f; int best = 0x7fffffff;
         for (int i = 0; i < kLanes; ++i) { S = fadd(S, s_f[tid][i]); best = min(best, s_i[tid][i]); }
+        s_sum[tid] = S; s_first[tid] = best;
+    }
+    cluster_sync_all();                   // every CTA's s_sum / s_first is visible cluster-wide
+    if (rank == 0 && tid < kNK) {
+        float S = s_sum[tid]; int best = s_first[tid];
+        for (unsigned r = 1; r < kCluster; ++r) {          // fixed order: CTA 0, 1, 2, 3
+            S = fadd(S, *peer_shared(&s_sum[tid], r));
+            best = min(best, *peer_shared(&s_first[tid], r));
+        }
         if (best == 0x7fffffff) best = 0;    // only with NaN logits
-        const float r = fdiv(1.0f, S);
+        const float rcp = fdiv(1.0f, S);
         const size_t o = (size_t)n * kNK + tid;
-        scores[o] = fmul(1.0f, r);
+        scores[o] = fmul(1.0f, rcp);
         positions[o * 2 + 0] = fdiv((float)(best / crop_w), (float)crop_h);
         positions[o * 2 + 1] = fdiv((float)(best % crop_w), (float)crop_w);
         if (argmax_out) argmax_out[o] = best;
     }
+    cluster_sync_all();                   // peers stay alive until CTA 0 has read their shared memory
 }
 
 }  // namespace
@@ -90,9 +133,10 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
                            float *scores, float *positions, int *argmax, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
-    if (crop_h * crop_w > kMaxPerThread * kLanes) return -(int)cudaErrorInvalidValue;
+    if (crop_h * crop_w > kMaxPerThread * kLanes * kCluster) return -(int)cudaErrorInvalidValue;
     prof_mark(s, "keypoint_decode");
-    keypoint_decode_kernel<<<n_max, kThreads, 0, s>>>(logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
+    keypoint_decode_kernel<<<n_max * kCluster, kThreads, 0, s>>>(logits, n_dev, n_host, crop_h, crop_w, scores, positions,
+                                                                argmax);
     return 1;
 }
 

@@ -200,6 +200,9 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tma_load_2d(stage + kWTileBytes + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
             }
             stamp(args, 1);                                                 // all fc1 loads issued
+            // (An L2 prefetch of the whole W2 tile at this point was measured: phase 3 got 2 us shorter but the two grid
+            // barriers 2 us longer -- the prefetch traffic delays the partial-sum stores and the barrier atomics -- so
+            // the run-ahead is limited to the shared-memory ring.)
             // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces
             const int first2 = it;
             int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
