@@ -29,7 +29,16 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU legs (rank 0 only) are meant to use all host cores, and the
+# OpenMP runtimes read the variable when they are first loaded -- so fix it before numpy / torch / the oracle are imported.
+if int(os.environ.get("RANK", "0")) == 0:
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+os.environ["NCCL_DEBUG"] = os.environ.get("MPN_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -45,8 +54,8 @@ HIDDEN = 1024
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--prn-mode", default="bf16", choices=["bf16", "fp32"])
@@ -65,7 +74,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -147,6 +156,7 @@ def cpu_port_runner(wl, weights):
     import torch
 
     import oracle
+    torch.set_num_threads(host_cores())
     W1, b1, W2, b2 = [torch.from_numpy(np.ascontiguousarray(a)) for a in weights]
 
     def prn_fn(x):
@@ -290,6 +300,11 @@ def main():
     if sampler:
         sampler.mark(t0, t1)
     _, launches1 = det.launch_count()
+    n_launches = int(launches1 - launches0)
+    if world > 1:
+        t = torch.tensor([n_launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_launches = int(t.item())
     dev_ms = e0.elapsed_time(e1)
     persons = int(out["person_offsets"][-1].item())
     if world > 1:
@@ -374,8 +389,13 @@ def main():
         top = max([n for n in order if kernels[n]["alg_bytes"]], key=lambda n: statistics.mean(acc[n]))
         ab = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
         ach = ab / statistics.mean(acc[top]) / 1e6
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        except Exception:
+            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": which,
+                    "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": which,
                     "alg_bytes_per_launch": ab, "avg_launch_ms": round(statistics.mean(acc[top]), 5),
                     "persons_per_batch": persons, "candidates_per_batch": n_cand}
 
@@ -402,7 +422,7 @@ def main():
                 "input_bytes_per_step": in_bytes,
                 "note": "class logits and heatmap logits are copied by DMA; the box codes stay in pinned host memory "
                         "and only the rows of confident anchors are gathered over PCIe by the NMS kernel"},
-        "gpu_launches": int(launches1 - launches0),
+        "gpu_launches": n_launches,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
     }
     print(json.dumps(line), flush=True)
