@@ -202,6 +202,10 @@ MPN_API int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n,
 MPN_API int mpn_set_profiling(mpn_handle *h, int32_t enable);
 MPN_API int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names, float *ms, int32_t *count);
 
+/* Development aid for timing experiments: stages whose bit is set are NOT launched by mpn_run (their outputs keep the
+ * values of the previous call): 1 detect, 2 heatmap, 4 normalise, 8 crop, 16 PRN, 32 keypoint decode.  0 = normal. */
+MPN_API int mpn_debug_skip(mpn_handle *h, uint32_t mask);
+
 /* Development aid: globaltimer stamps (ns) of the phases of the most recent single-kernel PRN launch, 16 slots per CTA:
  * 0 prologue, 1 fc1 loads issued, 2 fc1 MMAs issued, 3 fc1 accumulators complete, 4 partials stored, 5 barrier 1 passed,
  * 8 y1 slice stored, 6 producer past barrier 2, 9 fc2 accumulators complete, 10 logits stored.  Synchronises the device. */

@@ -156,7 +156,8 @@ struct ProfScope {
 };
 
 int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores, int *num_boxes,
-              int *sel_anchor, int *n_candidates, int *offsets_out, cudaStream_t s, bool first)
+              int *sel_anchor, int *n_candidates, int *offsets_out, cudaStream_t s, bool first,
+              cudaEvent_t after_candidates = nullptr)
 {
     int rc = check_image_size(h, in->batch, in->height, in->width);
     if (rc) return rc;
@@ -202,7 +203,7 @@ int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *b
     a.person_img = h->person_img;
     a.person_offsets = h->person_offsets;
     a.person_offsets_out = offsets_out;
-    return launched(h, launch_detect(t, a, s), first, "detect");
+    return launched(h, launch_detect(t, a, s, after_candidates), first, "detect");
 }
 
 int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const int *n_dev, int n_host, int n_max,
@@ -363,13 +364,23 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     cudaMemset(h->cand_count, 0, B * sizeof(int));
     cudaMemset(h->person_offsets, 0, (B + 1) * sizeof(int));
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
+        e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->own_event, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cand, cudaEventDisableTiming);
     h->cfg_use_graphs = getenv("MPN_NO_GRAPH") == nullptr;
     if (e != cudaSuccess) {
         fail(nullptr, MPN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+        mpn_destroy(h);
+        return MPN_ERR_CUDA;
+    }
+    if (kpdecode_prepare(h->own_stream) != 0 || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
+        fail(nullptr, MPN_ERR_CUDA, "keypoint decode setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         mpn_destroy(h);
         return MPN_ERR_CUDA;
     }
@@ -415,6 +426,7 @@ void mpn_destroy(mpn_handle *h)
     if (h->own_event) cudaEventDestroy(h->own_event);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_cand) cudaEventDestroy(h->ev_cand);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     delete h;
@@ -554,44 +566,59 @@ int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *s
     return launched(h, launch_test_math(x, y, n, 1, (cudaStream_t)stream), true, "test sigmoid");
 }
 
-// Enqueues every kernel of the path.  With `fork` the two independent front halves run concurrently: candidates ->
-// sort/NMS -> person list on `s`, heatmap activation -> normalisation on the handle's auxiliary stream, joined before
-// the crops (the same code is what gets captured into a CUDA graph).
+// Enqueues every kernel of the path.  With `fork` the two independent front halves run concurrently: heatmap activation
+// -> normalisation (thousands of short CTAs) on `s`, candidates -> sort/NMS -> person list (a few latency-bound CTAs) on
+// the handle's HIGH-PRIORITY auxiliary stream so that its CTAs are placed as soon as heatmap CTAs retire instead of
+// queueing behind the whole heatmap grid; joined before the crops.  The same code is what gets captured into a CUDA graph
+// (kernel nodes inherit the stream priority).
 static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, cudaStream_t s,
                         bool fork)
 {
-    cudaStream_t sa = fork ? h->aux_stream : s;
+    cudaStream_t sd = fork ? h->aux_stream : s;     // detect branch
+    cudaStream_t sa = s;                            // heatmap branch
     if (fork) {
         MPN_CUDA(h, cudaEventRecord(h->ev_fork, s));
-        MPN_CUDA(h, cudaStreamWaitEvent(sa, h->ev_fork, 0));
+        MPN_CUDA(h, cudaStreamWaitEvent(sd, h->ev_fork, 0));
     }
+    const unsigned skip = h->debug_skip;
+    int rc = MPN_OK;
     // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
-    int rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, s, true);
+    // The heatmap grid (thousands of CTAs) is released only once the candidate scan has finished, i.e. at the moment
+    // sort/NMS becomes ready as well: its 8 big CTAs (512 threads, 64 registers) are placed first on an empty GPU and the
+    // heatmap CTAs fill the other SMs.  Released together with the candidate scan they would occupy every SM for their
+    // whole 2.7 waves and sort/NMS would start only when they drain (measured: no overlap at all).
+    if (!(skip & 1u))
+        rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, sd, true,
+                       fork ? h->ev_cand : nullptr);
     if (rc) return rc;
+    if (fork) {
+        MPN_CUDA(h, cudaEventRecord(h->ev_join, sd));
+        if (!(skip & 1u)) MPN_CUDA(h, cudaStreamWaitEvent(sa, h->ev_cand, 0));
+    }
     // 2. heatmap sigmoid / split / min-max, then normalise the whole map once   (create_pb.py:73-76, 90-94)
     const int hh = in->height / h->cfg.downsample, ww = in->width / h->cfg.downsample;
     float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
-    rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
-                                     nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
+    if (!(skip & 2u))
+        rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
+                                         nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
     if (rc) return rc;
-    rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
+    if (!(skip & 4u)) rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
     if (rc) return rc;
-    if (fork) {
-        MPN_CUDA(h, cudaEventRecord(h->ev_join, sa));
-        MPN_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-    }
+    if (fork) MPN_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     // 3. crop_and_resize                                     (create_pb.py:106-109)
     const int n_max = in->batch * p->max_detections;
     const int *n_dev = h->person_offsets + in->batch;
     const bool bf16 = p->prn_mode == MPN_PRN_BF16;
-    rc = launched(h, launch_crop(h->nh_ws, nullptr, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
-                                 h->cfg.crop_height, h->cfg.crop_width, h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
-                  false, "crop");
+    if (!(skip & 8u))
+        rc = launched(h, launch_crop(h->nh_ws, nullptr, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
+                                     h->cfg.crop_height, h->cfg.crop_width, h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
+                      false, "crop");
     if (rc) return rc;
     // 4. PRN                                                 (detector/prn.py:5-25)
-    rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, h->logits, s, false);
+    if (!(skip & 16u)) rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, h->logits, s, false);
     if (rc) return rc;
     // 5. softmax / argmax                                    (create_pb.py:115-142)
+    if (skip & 32u) return MPN_OK;
     return launched(h, launch_keypoint_decode(h->logits, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
                                               out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
                     "keypoint decode");
@@ -619,6 +646,7 @@ static void make_graph_key(const mpn_handle *h, const mpn_inputs *in, const mpn_
     const void *ptrs[8] = {out->boxes, out->scores, out->num_boxes, out->keypoint_heatmaps, out->segmentation_masks,
                            out->keypoint_scores, out->keypoint_positions, out->person_offsets};
     for (int i = 0; i < 8; ++i) k->v[o++] = (uint64_t)(uintptr_t)ptrs[i];
+    k->v[0] |= (uint64_t)h->debug_skip << 32;
 }
 
 static int run_graphed(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, cudaStream_t s)
@@ -845,6 +873,13 @@ int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int
     const int rc = prn_fused_trace(h, enable, reinterpret_cast<unsigned long long *>(host_out), capacity, &g);
     if (grid_out) *grid_out = g;
     return rc == MPN_OK ? MPN_OK : fail(h, rc, "fused PRN trace unavailable");
+}
+
+int mpn_debug_skip(mpn_handle *h, uint32_t mask)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    h->debug_skip = mask;
+    return MPN_OK;
 }
 
 int mpn_set_profiling(mpn_handle *h, int32_t enable)

@@ -78,7 +78,8 @@ inline void prof_mark(cudaStream_t s, const char *name)
 
 // ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
-int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s);
+// after_candidates (optional): event recorded on `s` between the candidate scan and the sort / NMS kernel
+int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates = nullptr);
 
 int heatmap_chunks_per_image(int B, int hh, int ww);
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
@@ -90,6 +91,7 @@ int launch_crop(const float *kh, const float *minmax, int hh, int ww, const floa
 int launch_get_keypoints(const float *hm, int hh, int ww, double ymin, double xmin, double ymax, double xmax,
                          double threshold, int *out, cudaStream_t s);
 
+int kpdecode_prepare(cudaStream_t s);   // once per device before the first decode (bisects the exp == 1 threshold)
 int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
                            float *scores, float *positions, int *argmax, cudaStream_t s);
 

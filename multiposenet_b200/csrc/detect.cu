@@ -341,7 +341,7 @@ int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
     return 1;
 }
 
-int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
+int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -362,6 +362,7 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s)
         candidates_nchw_kernel<<<grid, 256, 0, s>>>(t, a);
     }
     ++launches;
+    if (after_candidates) cudaEventRecord(after_candidates, s);
     prof_mark(s, "sort_nms");
     sort_nms_kernel<<<a.B, kNmsThreads, sizeof(NmsSmem), s>>>(t, a);
     ++launches;

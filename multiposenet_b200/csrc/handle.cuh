@@ -30,11 +30,12 @@ struct mpn_handle {
     int max_anchors, key_cap, max_hm_pix, max_persons;
     char err[512];
     cudaStream_t own_stream, aux_stream;
-    cudaEvent_t own_event, ev_fork, ev_join;
+    cudaEvent_t own_event, ev_fork, ev_join, ev_cand;
     // CUDA graphs of mpn_run, keyed by the call's pointers / shapes / parameters
     mpn::GraphEntry graphs[mpn::kGraphCache];
     uint64_t graph_clock;
     bool cfg_use_graphs, graphs_disabled;
+    unsigned debug_skip;    // mpn_debug_skip: bit i set = stage i is not launched (timing experiments only)
     // detect workspace
     unsigned long long *cand_keys;
     int *cand_count;

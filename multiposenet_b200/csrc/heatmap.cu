@@ -39,13 +39,22 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
     __shared__ int s_min[kNK], s_max[kNK];
     __shared__ int s_last;
     const int img = blockIdx.y, tid = threadIdx.x;
-    int ooff[4];          // output element offset inside the tile: kh index (pixel*17 + c), or -(pixel + 1) for the mask
+    // Straight-line inner code: every element gets the sigmoid (1 in 18 is the mask channel and keeps its raw value by a
+    // select), every element has ONE precomputed destination (its keypoint_heatmaps slot, or its segmentation_masks slot),
+    // and the mask channel's min / max registers are simply never merged.  No divergence inside a warp.
     int ch[4];
+    bool is_kp[4];
+    float *dst[4];                         // destination of element j in tile 0 of this image
+    int dst_step[4];                       // ... and its stride from one tile to the next
+    float *kh_img = kh + (size_t)img * npix * kNK;
+    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int e = 4 * tid + j, p = e / kCH;
         ch[j] = e - p * kCH;
-        ooff[j] = ch[j] < kNK ? p * kNK + ch[j] : -(p + 1);
+        is_kp[j] = ch[j] < kNK;
+        dst[j] = is_kp[j] ? kh_img + p * kNK + ch[j] : (seg_img ? seg_img + p : nullptr);
+        dst_step[j] = is_kp[j] ? kHmPix * kNK : kHmPix;
     }
     float mn[4], mx[4];
 #pragma unroll
@@ -53,29 +62,21 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
     if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
 
     const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
-    float *kh_img = kh + (size_t)img * npix * kNK;
-    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
     // npix is a multiple of 64 on this path (images are multiples of 128): every tile is full.  Two tiles per trip.
     for (int tile = blockIdx.x; tile < tiles_per_img; tile += 2 * gridDim.x) {
         const int tile2 = tile + gridDim.x;
         const bool two = tile2 < tiles_per_img;
         const float4 qa = __ldcs(src + (size_t)tile * kHmThreads + tid);
         const float4 qb = two ? __ldcs(src + (size_t)tile2 * kHmThreads + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
+        const float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (ch[j] < kNK) {
-                va[j] = exact_sigmoidf(va[j]);
-                mn[j] = fminf(mn[j], va[j]); mx[j] = fmaxf(mx[j], va[j]);
-                kh_img[(size_t)tile * kHmPix * kNK + ooff[j]] = va[j];
-                if (two) {
-                    vb[j] = exact_sigmoidf(vb[j]);
-                    mn[j] = fminf(mn[j], vb[j]); mx[j] = fmaxf(mx[j], vb[j]);
-                    kh_img[(size_t)tile2 * kHmPix * kNK + ooff[j]] = vb[j];
-                }
-            } else if (seg_img) {
-                seg_img[(size_t)tile * kHmPix - ooff[j] - 1] = va[j];
-                if (two) seg_img[(size_t)tile2 * kHmPix - ooff[j] - 1] = vb[j];
+            const float sa = exact_sigmoidf(va[j]), sb = exact_sigmoidf(vb[j]);
+            mn[j] = fminf(mn[j], sa); mx[j] = fmaxf(mx[j], sa);
+            if (two) { mn[j] = fminf(mn[j], sb); mx[j] = fmaxf(mx[j], sb); }
+            if (dst[j]) {
+                dst[j][(size_t)tile * dst_step[j]] = is_kp[j] ? sa : va[j];
+                if (two) dst[j][(size_t)tile2 * dst_step[j]] = is_kp[j] ? sb : vb[j];
             }
         }
     }

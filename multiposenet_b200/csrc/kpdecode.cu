@@ -12,7 +12,11 @@
 // argmax rule, bit-matched to the oracle without depending on the summation order of the denominator:
 // p[i] = e[i] * r with r = 1/sum and e[i] = exp(l[i] - lmax) <= 1.  e[i] * r == r iff e[i] == 1.0f (for e[i] <= 1 - 2^-24
 // the product is at least half an ulp below r and rounds to a smaller float), so the first index with maximal
-// probability is the first index whose e[i] is exactly 1.0f.  keypoint_scores = 1.0f * r.
+// probability is the first index whose e[i] is exactly 1.0f.  The exp recipe is monotone near 0, so "exp(d) == 1.0f"
+// is the comparison d >= x0 with x0 the most negative float whose recipe value is 1.0f (found once per device by
+// bisection with the recipe itself, kpdecode_prepare): the decision costs one subtraction and one compare per logit.
+// keypoint_scores = 1 / sum is only held to 1e-4, so the 2016-term sum uses the hardware ex2 approximation (~2 ulp per
+// term) instead of the 20-instruction exact recipe -- the kernel was instruction-issue bound on it.
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -25,6 +29,19 @@ constexpr int kLanes = 32;
 constexpr int kThreads = kNK * kLanes;   // 544
 constexpr int kCluster = 4;
 constexpr int kMaxPerThread = 16;        // positions per thread: ceil(2048 / 4 / 32)
+
+__device__ float g_exp_one_x0;     // most negative x with exact_expf(x) == 1.0f
+
+__global__ void exp_one_threshold_kernel()
+{
+    // negative floats are ordered by their magnitude bits: bisect the largest magnitude that still gives exactly 1.0f
+    unsigned lo = 0x80000000u, hi = 0xBF800000u;      // -0.0f (gives 1) .. -1.0f (does not)
+    while (hi - lo > 1u) {
+        const unsigned mid = lo + (hi - lo) / 2u;
+        if (exact_expf(__uint_as_float(mid)) == 1.0f) lo = mid; else hi = mid;
+    }
+    g_exp_one_x0 = __uint_as_float(lo);
+}
 
 __device__ __forceinline__ unsigned cluster_rank()
 {
@@ -75,12 +92,14 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
         v[i] = (p < p1) ? __ldcs(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
         lmax = fmaxf(lmax, v[i]);
     }
+    const int warp = tid >> 5, lane = tid & 31;       // 17 warps: warp w folds the 32 partials of channel w
     s_f[c][q] = lmax;
     __syncthreads();
-    if (tid < kNK) {
-        float m = s_f[tid][0];
-        for (int i = 1; i < kLanes; ++i) m = fmaxf(m, s_f[tid][i]);
-        s_max[tid] = m;
+    {
+        float m = s_f[warp][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_max[warp] = m;
     }
     cluster_sync_all();                   // every CTA's s_max is visible cluster-wide
     if (tid < kNK) {
@@ -91,23 +110,28 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
     }
     __syncthreads();
     lmax = s_gmax[c];
+    const float x0 = g_exp_one_x0;
     float sum = 0.0f;
     int first = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < kMaxPerThread; ++i) {
         const int p = p0 + q + kLanes * i;
         if (p < p1) {
-            const float e = exact_expf(fsub(v[i], lmax));
-            sum = fadd(sum, e);
-            if (e == 1.0f && p < first) first = p;
+            const float d = fsub(v[i], lmax);
+            sum = fadd(sum, __expf(d));
+            if (d >= x0 && p < first) first = p;       // <=> exact_expf(d) == 1.0f
         }
     }
     s_f[c][q] = sum; s_i[c][q] = first;
     __syncthreads();
-    if (tid < kNK) {
-        float S = 0.0f; int best = 0x7fffffff;
-        for (int i = 0; i < kLanes; ++i) { S = fadd(S, s_f[tid][i]); best = min(best, s_i[tid][i]); }
-        s_sum[tid] = S; s_first[tid] = best;
+    {
+        float S = s_f[warp][lane]; int best = s_i[warp][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {          // butterfly: a fixed summation tree
+            S = fadd(S, __shfl_xor_sync(0xffffffffu, S, o));
+            best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (lane == 0) { s_sum[warp] = S; s_first[warp] = best; }
     }
     cluster_sync_all();                   // every CTA's s_sum / s_first is visible cluster-wide
     if (rank == 0 && tid < kNK) {
@@ -128,6 +152,12 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
 }
 
 }  // namespace
+
+int kpdecode_prepare(cudaStream_t s)
+{
+    exp_one_threshold_kernel<<<1, 1, 0, s>>>();
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
                            float *scores, float *positions, int *argmax, cudaStream_t s)

@@ -454,6 +454,11 @@ class Detector:
         self._check(self._lib.mpn_debug_fused_trace(self._handle, 1 if enable else 0, buf, cap, C.byref(g)))
         return np.frombuffer(buf, dtype=np.uint64, count=g.value * 16).reshape(g.value, 16).copy()
 
+    def debug_skip(self, mask):
+        """Development aid (mpn_debug_skip): do not launch the stages whose bit is set (1 detect, 2 heatmap, 4 normalise,
+        8 crop, 16 PRN, 32 keypoint decode); their outputs keep the previous call's values."""
+        self._check(self._lib.mpn_debug_skip(self._handle, int(mask)))
+
     def launch_count(self):
         last, total = C.c_int64(0), C.c_int64(0)
         self._lib.mpn_launch_count(self._handle, C.byref(last), C.byref(total))
