@@ -226,6 +226,9 @@ int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const
         if (rc || n_max <= kPrnFusedMaxRows) return rc;
         first = false;
     }
+    if (h->big)
+        return launched(h, launch_prn_big(h, x_f32, n_dev, n_host, n_max, logits, h->fused ? kPrnFusedMaxRows : 0, s), first,
+                        "prn big");
     return launched(h, launch_prn_bf16(w, h->prn_ws, x_f32, x_bf16, n_dev, n_host, n_max, logits, h->tmaps,
                                        h->fused ? kPrnFusedMaxRows : 0, s), first, "prn bf16");
 }
@@ -387,6 +390,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     if (cfg->prn_modes & 2) {
         int rc = prn_bf16_prepare(h);
         if (rc == MPN_OK) rc = prn_fused_prepare(h);
+        if (rc == MPN_OK && getenv("MPN_NO_BIG_GEMM") == nullptr) rc = prn_big_prepare(h);
         if (rc != MPN_OK) {
             snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
             mpn_destroy(h);
@@ -404,6 +408,7 @@ void mpn_destroy(mpn_handle *h)
     cudaDeviceSynchronize();
     prn_bf16_release(h);
     prn_fused_release(h);
+    prn_big_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
                     h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_counter, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};

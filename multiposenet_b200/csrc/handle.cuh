@@ -57,6 +57,7 @@ struct mpn_handle {
     mpn::PrnWorkspace prn_ws;
     void *tmaps;            // opaque: prn_tcgen05.cu
     void *fused;            // opaque: prn_fused.cu (NULL when the shape is not covered)
+    void *big;              // opaque: prn_big.cu (NULL when the shape is not covered or the capacity is <= 256 persons)
     bool have_weights;
     // host path (mpn_submit_host): kHostSlots calls in flight, copy-in / compute / copy-out on three streams
     mpn::HostSlot slots[mpn::kHostSlots];
@@ -72,6 +73,10 @@ struct mpn_handle {
 namespace mpn {
 int prn_bf16_prepare(mpn_handle *h);   // prn_tcgen05.cu: TMA tensor maps for the bf16 GEMMs
 void prn_bf16_release(mpn_handle *h);
+int prn_big_prepare(mpn_handle *h);    // prn_big.cu: persistent tcgen05 GEMMs for > kPrnFusedMaxRows persons
+void prn_big_release(mpn_handle *h);
+int launch_prn_big(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, int n_max, float *logits, int skip_le,
+                   cudaStream_t s);
 int prn_fused_prepare(mpn_handle *h);  // prn_fused.cu: persistent single-kernel PRN for <= kPrnFusedMaxRows persons
 void prn_fused_release(mpn_handle *h);
 int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int capacity, int *grid_out);

@@ -304,11 +304,15 @@ __global__ void minmax_copy_kernel(const float *ws, float *out, int n)
 
 int heatmap_chunks_per_image(int B, int hh, int ww)
 {
-    // two 64-pixel tiles per CTA, one trip: every load of the kernel is issued in the first few hundred cycles of a
-    // CTA's life and the many resident CTAs per SM hide the HBM latency and the sigmoid dependency chains
-    (void)B;
+    // Two 64-pixel tiles per trip.  Small calls: one trip per CTA (every load of the kernel is issued in the first few
+    // hundred cycles of a CTA's life, many resident CTAs hide the HBM latency).  Large calls: about six CTAs per SM, each
+    // making a whole number of trips, so that the per-thread set-up (channel pattern, destinations) is amortised.
     const int tiles = (hh * ww + kHmPix - 1) / kHmPix;
-    return (tiles + 1) / 2;
+    const long long pairs = ((long long)tiles * B + 1) / 2;
+    long long trips = (pairs + 148 * 6 / 2) / (148 * 6);
+    if (trips < 1) trips = 1;
+    const int per_img = (int)((tiles + 2 * trips - 1) / (2 * trips));
+    return per_img < 1 ? 1 : per_img;
 }
 
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,

@@ -121,25 +121,6 @@ __device__ __forceinline__ void stamp(const FusedArgs &a, int slot)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-// Per-warp 32 x 16 fp32 transpose through shared memory: the accumulator arrives one ROW per lane (tcgen05.ld 32x32b.x16),
-// global memory wants one 64-byte row segment per 4 lanes.  16-byte chunks are XOR-swizzled by ((row >> 1) & 3) so that
-// both the row-per-lane writes and the 4-lanes-per-row reads are bank-conflict free.
-__device__ __forceinline__ void stage_write(float *stg, int lane, const uint32_t (&r)[16])
-{
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4 *>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                        __uint_as_float(r[4 * j + 3]));
-}
-
-// i-th of the 4 coalesced passes: lane -> (row 8 i + lane / 4, columns 4 (lane % 4) ..)
-__device__ __forceinline__ float4 stage_read(const float *stg, int lane, int i)
-{
-    const int row = 8 * i + (lane >> 2), j = lane & 3;
-    return *reinterpret_cast<const float4 *>(stg + row * 16 + ((j ^ ((row >> 1) & 3)) << 2));
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,

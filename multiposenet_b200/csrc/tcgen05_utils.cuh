@@ -107,6 +107,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 }
 
 
+// Per-warp 32 x 16 fp32 transpose through shared memory: the accumulator arrives one ROW per lane (tcgen05.ld 32x32b.x16),
+// global memory wants one 64-byte row segment per 4 lanes.  16-byte chunks are XOR-swizzled by ((row >> 1) & 3) so that
+// both the row-per-lane writes and the 4-lanes-per-row reads are bank-conflict free.
+__device__ __forceinline__ void stage_write(float *stg, int lane, const uint32_t (&r)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4 *>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+}
+
+// i-th of the 4 coalesced passes: lane -> (row 8 i + lane / 4, columns 4 (lane % 4) ..)
+__device__ __forceinline__ float4 stage_read(const float *stg, int lane, int i)
+{
+    const int row = 8 * i + (lane >> 2), j = lane & 3;
+    return *reinterpret_cast<const float4 *>(stg + row * 16 + ((j ^ ((row >> 1) & 3)) << 2));
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot_in_smem, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols)

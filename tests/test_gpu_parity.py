@@ -235,7 +235,7 @@ def test_prn_fp32_within_1e4(det6, prn_weights, n):
     np.testing.assert_allclose(got, want, rtol=RTOL_FP32, atol=RTOL_FP32 * np.abs(want).max())
 
 
-@pytest.mark.parametrize("n", [1, 5, 130, 256, 300])
+@pytest.mark.parametrize("n", [1, 5, 130, 256, 300, 600])
 def test_prn_bf16_tcgen05_within_1e2_and_close_to_bf16_oracle(det6, prn_weights, n):
     x = synthetic.make_crops(n, seed=31 + n)
     got = det6.prn(_cuda(x), "bf16").cpu().numpy()
@@ -243,6 +243,21 @@ def test_prn_bf16_tcgen05_within_1e2_and_close_to_bf16_oracle(det6, prn_weights,
     assert _rel_err(got, exact) < RTOL_BF16                     # the north_star bar
     emul = oracle.prn(x, *prn_weights, mode=1)                  # same operand rounding, fp64 accumulate
     assert _rel_err(got, emul) < 2e-3                           # what is left is accumulation order + y1 rounding flips
+
+
+def test_prn_tiled_fallback_kernels(prn_weights, monkeypatch):
+    """prn_tcgen05.cu (non-persistent 128 x 128 / 128 x 96 tiles) is the fallback for shapes the persistent large-batch
+    kernels do not cover; MPN_NO_BIG_GEMM forces it so that it stays tested."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    monkeypatch.setenv("MPN_NO_BIG_GEMM", "1")
+    det = Detector(prn_weights, DetectorConfig(max_batch=4, max_boxes=128, prn_mode="bf16", prn_modes_allocated=("bf16",)))
+    try:
+        x = synthetic.make_crops(300, seed=77)
+        got = det.prn(_cuda(x), "bf16").cpu().numpy()
+        emul = oracle.prn(x, *prn_weights, mode=1)
+        assert _rel_err(got, emul) < 2e-3
+    finally:
+        det.close()
 
 
 def test_prn_known_answers(prn_weights):
