@@ -334,7 +334,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     MPN_ALLOC(h->person_img, NP);
     MPN_ALLOC(h->person_offsets, B + 1);
     MPN_ALLOC(h->kh_ws, B * h->max_hm_pix * 17);
-    MPN_ALLOC(h->nh_ws, B * h->max_hm_pix * 17);
+    MPN_ALLOC(h->nh_ws, B * h->max_hm_pix * 20);   // padded pixels (heatmap.cu: kPadCh)
     MPN_ALLOC(h->minmax_ws, B * 17 * 2);
     MPN_ALLOC(h->hm_partial, B * (size_t)((h->max_hm_pix / 64 + 1) / 2 + 1) * 17 * 2);
     MPN_ALLOC(h->hm_counter, B);
@@ -607,7 +607,10 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
         rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
                                          nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
     if (rc) return rc;
-    if (!(skip & 4u)) rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
+    // crop sizes the padded-map kernel does not cover fall back to per-tap normalisation of the 17-channel map
+    const bool padded = crop_padded_supported(h->cfg.crop_height, h->cfg.crop_width);
+    if (!(skip & 4u) && padded)
+        rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
     if (rc) return rc;
     if (fork) MPN_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     // 3. crop_and_resize                                     (create_pb.py:106-109)
@@ -615,8 +618,12 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     const int *n_dev = h->person_offsets + in->batch;
     const bool bf16 = p->prn_mode == MPN_PRN_BF16;
     if (!(skip & 8u))
-        rc = launched(h, launch_crop(h->nh_ws, nullptr, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
-                                     h->cfg.crop_height, h->cfg.crop_width, h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
+        rc = launched(h, padded ? launch_crop_padded(h->nh_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
+                                                     h->cfg.crop_height, h->cfg.crop_width, h->crops_f32,
+                                                     bf16 ? h->crops_bf16 : nullptr, s)
+                                : launch_crop(kh, h->minmax_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
+                                              h->cfg.crop_height, h->cfg.crop_width, h->crops_f32,
+                                              bf16 ? h->crops_bf16 : nullptr, s),
                       false, "crop");
     if (rc) return rc;
     // 4. PRN                                                 (detector/prn.py:5-25)

@@ -85,6 +85,10 @@ int heatmap_chunks_per_image(int B, int hh, int ww);
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
                     float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s);
 int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s);
+// crop of the padded (20 floats / pixel) normalised workspace written by launch_normalise
+bool crop_padded_supported(int crop_h, int crop_w);
+int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,
+                       int n_max, int crop_h, int crop_w, float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s);
 int launch_crop(const float *kh, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
                 const int *n_dev, int n_host, int n_max, int crop_h, int crop_w, float *crops_f32,
                 __nv_bfloat16 *crops_bf16, cudaStream_t s);

@@ -122,34 +122,141 @@ __device__ __forceinline__ float normalise_tap(float v, float m, float M, float 
     return fmul(fdiv(fsub(v, m), fsub(M, m)), mask);
 }
 
-// create_pb.py:93-94 over the whole map: nh = (kh - m) / (M - m) * float(M > 0.2), float4 at a time.  Normalising every
-// heatmap pixel once costs one division per pixel; normalising the four taps of every crop sample costs 4 N D divisions,
-// which is 3x (config 2) to 30x (crowded scenes) more.  grid = (chunks, B), every CTA stays inside one image.
+// create_pb.py:93-94 over the whole map: nh = (kh - m) / (M - m) * float(M > 0.2).  Normalising every heatmap pixel once
+// costs one division per pixel; normalising the four taps of every crop sample costs 4 N D divisions, which is 3x
+// (config 2) to 30x (crowded scenes) more.  The normalised map is a private workspace, so its pixels are PADDED to 20
+// floats (80 bytes): the crop kernel then fetches a tap's channels as aligned 16-byte vectors, 5 per pixel (it is bound
+// by L1 throughput and instruction issue; scalar taps cost 4x the load instructions and wavefronts).
+// One thread per (pixel, group of 4 channels); grid = (chunks, B).
+constexpr int kPadCh = 20;
+constexpr int kGroups = kPadCh / 4;
 __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
-                                                        const int n4_per_img, float *__restrict__ nh)
+                                                        const int npix, float *__restrict__ nh)
 {
-    __shared__ float s_m[kNK], s_d[kNK], s_mask[kNK];
+    __shared__ float s_m[kPadCh], s_d[kPadCh], s_mask[kPadCh];
     const int img = blockIdx.y;
-    if (threadIdx.x < kNK) {
-        const float m = __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2);
-        const float M = __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2 + 1);
+    if (threadIdx.x < kPadCh) {
+        const bool real = threadIdx.x < kNK;
+        const float m = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2) : 0.0f;
+        const float M = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2 + 1) : 1.0f;
         s_m[threadIdx.x] = m;
         s_d[threadIdx.x] = fsub(M, m);
-        s_mask[threadIdx.x] = (M > 0.2f) ? 1.0f : 0.0f;
+        s_mask[threadIdx.x] = (real && M > 0.2f) ? 1.0f : 0.0f;
     }
     __syncthreads();
-    const float4 *src = reinterpret_cast<const float4 *>(kh) + (size_t)img * n4_per_img;
-    float4 *dst = reinterpret_cast<float4 *>(nh) + (size_t)img * n4_per_img;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_img; i += gridDim.x * blockDim.x) {
-        const float4 v = __ldcg(src + i);
-        int c = (int)((4u * (unsigned)i) % (unsigned)kNK);
-        float o[4] = {v.x, v.y, v.z, v.w};
+    const float *src = kh + (size_t)img * npix * kNK;
+    float4 *dst = reinterpret_cast<float4 *>(nh + (size_t)img * npix * kPadCh);
+    const int total = npix * kGroups;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = i / kGroups, g = i - p * kGroups;
+        float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            o[k] = fmul(fdiv(fsub(o[k], s_m[c]), s_d[c]), s_mask[c]);
-            c = (c + 1 == kNK) ? 0 : c + 1;
+            const int c = 4 * g + k;
+            const float v = c < kNK ? __ldcg(src + (size_t)p * kNK + c) : 0.0f;
+            o[k] = c < kNK ? fmul(fdiv(fsub(v, s_m[c]), s_d[c]), s_mask[c]) : 0.0f;
         }
         dst[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// crop_and_resize of the PADDED normalised map (the path of mpn_run): same geometry table as crop_kernel below, but every
+// thread takes one (crop pixel, group of 4 channels): four aligned 16-byte tap loads, 12 lerps, and the four results go
+// to a shared-memory image of the band, which is then written out in memory order as 16-byte (fp32) and 8-byte (bf16)
+// vectors.
+struct __align__(16) PixTabP {
+    int p_tl, p_tr, p_bl, p_br;      // source pixel indices of the four taps; p_tl < 0: extrapolated (output 0)
+    float lx, ly, pad0, pad1;
+};
+constexpr int kCropPBands = 14;
+constexpr int kCropPMaxPix = 160;     // 4 rows x 36 columns = 144 pixels per band
+
+__global__ void __launch_bounds__(256) crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww,
+                                                          const float *__restrict__ boxes, const int *__restrict__ box_ind,
+                                                          const int *__restrict__ n_dev, const int n_host, const int crop_h,
+                                                          const int crop_w, float *__restrict__ out_f32,
+                                                          __nv_bfloat16 *__restrict__ out_bf16)
+{
+    __shared__ PixTabP s_tab[kCropPMaxPix];
+    __shared__ __align__(16) float s_out[kCropPMaxPix * kNK];
+    const int n = blockIdx.x;
+    const int N = n_dev ? *n_dev : n_host;
+    if (n >= N) return;
+    const int rows_per_band = (crop_h + gridDim.y - 1) / gridDim.y;
+    const int cy0 = blockIdx.y * rows_per_band, cy1 = min(crop_h, cy0 + rows_per_band);
+    if (cy0 >= cy1) return;
+    const int npix = (cy1 - cy0) * crop_w;
+    const float4 box = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
+    const int b = __ldg(box_ind + n);
+    const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
+    const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const int cy = cy0 + p / crop_w, cx = p % crop_w;
+        float in_y, in_x;
+        if (crop_h > 1) {
+            const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(crop_h - 1));
+            in_y = fadd(fmul(y1, hm1), fmul((float)cy, hs));
+        } else {
+            in_y = fmul(fmul(0.5f, fadd(y1, y2)), hm1);
+        }
+        if (crop_w > 1) {
+            const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(crop_w - 1));
+            in_x = fadd(fmul(x1, wm1), fmul((float)cx, ws));
+        } else {
+            in_x = fmul(fmul(0.5f, fadd(x1, x2)), wm1);
+        }
+        PixTabP t;
+        const bool valid = !(in_y < 0.0f || in_y > hm1 || in_x < 0.0f || in_x > wm1);
+        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+        const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
+        t.p_tl = valid ? top * ww + left : -1;
+        t.p_tr = valid ? top * ww + right : 0;
+        t.p_bl = valid ? bot * ww + left : 0;
+        t.p_br = valid ? bot * ww + right : 0;
+        t.ly = fsub(in_y, (float)top); t.lx = fsub(in_x, (float)left);
+        t.pad0 = 0.0f; t.pad1 = 0.0f;
+        s_tab[p] = t;
+    }
+    __syncthreads();
+    const float *img = src + (size_t)b * hh * ww * kPadCh;
+    const int total = npix * kGroups;
+    for (int f = threadIdx.x; f < total; f += blockDim.x) {
+        const int p = f / kGroups, g = f - p * kGroups;
+        const int4 tp = *reinterpret_cast<const int4 *>(&s_tab[p].p_tl);
+        const float2 w = *reinterpret_cast<const float2 *>(&s_tab[p].lx);
+        float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (tp.x >= 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.x * kPadCh) + g);
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.y * kPadCh) + g);
+            const float4 cq = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.z * kPadCh) + g);
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.w * kPadCh) + g);
+            const float tl[4] = {a.x, a.y, a.z, a.w}, tr[4] = {bq.x, bq.y, bq.z, bq.w};
+            const float bl[4] = {cq.x, cq.y, cq.z, cq.w}, br[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float tpv = fadd(tl[k], fmul(fsub(tr[k], tl[k]), w.x));
+                const float btv = fadd(bl[k], fmul(fsub(br[k], bl[k]), w.x));
+                r[k] = fadd(tpv, fmul(fsub(btv, tpv), w.y));
+            }
+        }
+        float *so = s_out + p * kNK + 4 * g;
+        so[0] = r[0];
+        if (g < kGroups - 1) { so[1] = r[1]; so[2] = r[2]; so[3] = r[3]; }      // group 4 holds channel 16 only
+    }
+    __syncthreads();
+    const int D = crop_h * crop_w * kNK;
+    const size_t o0 = (size_t)n * D + (size_t)cy0 * crop_w * kNK;     // multiple of 4 floats (launch_crop checks)
+    const int n4 = npix * kNK / 4;
+    for (int f = threadIdx.x; f < n4; f += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4 *>(s_out)[f];
+        if (out_f32) reinterpret_cast<float4 *>(out_f32 + o0)[f] = v;
+        if (out_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const unsigned *>(&lo);
+            u.y = *reinterpret_cast<const unsigned *>(&hi);
+            reinterpret_cast<uint2 *>(out_bf16 + o0)[f] = u;
+        }
     }
 }
 
@@ -336,12 +443,12 @@ int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *s
 
 int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s)
 {
-    const int n4 = hh * ww * kNK / 4;        // hh * ww is a multiple of 64 on this path
+    const int total = hh * ww * kGroups;
     int per_img = (148 * 8 + B - 1) / B;
-    const int max_blocks = (n4 + 255) / 256;
+    const int max_blocks = (total + 255) / 256;
     if (per_img > max_blocks) per_img = max_blocks;
     prof_mark(s, "normalise");
-    normalise_kernel<<<dim3(per_img, B), 256, 0, s>>>(kh, minmax, n4, nh);
+    normalise_kernel<<<dim3(per_img, B), 256, 0, s>>>(kh, minmax, hh * ww, nh);
     return 1;
 }
 
@@ -360,6 +467,23 @@ int launch_crop(const float *src, const float *minmax, int hh, int ww, const flo
     prof_mark(s, "crop");
     crop_kernel<<<grid, 256, 0, s>>>(src, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32,
                                      crops_bf16);
+    return 1;
+}
+
+bool crop_padded_supported(int crop_h, int crop_w)
+{
+    const int rows = (crop_h + kCropPBands - 1) / kCropPBands;
+    return rows * crop_w <= kCropPMaxPix && (rows * crop_w * kNK) % 4 == 0 && (crop_h * crop_w * kNK) % 4 == 0;
+}
+
+int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,
+                       int n_max, int crop_h, int crop_w, float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s)
+{
+    if (n_max <= 0) return 0;
+    if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
+    dim3 grid(n_max, kCropPBands);
+    prof_mark(s, "crop");
+    crop_padded_kernel<<<grid, 256, 0, s>>>(nh, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32, crops_bf16);
     return 1;
 }
 
