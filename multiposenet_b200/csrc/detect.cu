@@ -161,7 +161,8 @@ struct NmsSmem {
     unsigned long long keys[kSortSmemCap];     // 64 KB: unsorted (rank sort source) or bitonic work area
     unsigned long long sorted[kRankSortCap];   //  8 KB: rank sort destination
     float4 box[kChunk];                        //  8 KB: decoded boxes of the current chunk
-    float4 kept_box[kMaxDetCap];               // 16 KB
+    NmsBox nbox[kChunk];                       // 10 KB: ... with ordered corners and area (pair tests)
+    NmsBox kept_nbox[kMaxDetCap];              // 20 KB
     int kept_local[kChunk];                    //  2 KB: chunk-local indices kept by step d
     unsigned alive[2][kMaskWords];             // live-candidate ballots, double buffered
 };
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
         // ---- a, b: decode, test against the boxes kept so far
         bool alive = tid < n;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        NmsBox nb = nms_prepare(box);
         float score = 0.f;
         int anchor = -1;
         if (alive) {
@@ -237,8 +239,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
             const Anchor an = anchor_from_index(t, anchor, &l, &loc, &k);
             box = decode_box(an, load_code(t, a, img, anchor, l, loc, k), t.sf);
             sm.box[tid] = box;
+            nb = nms_prepare(box);
+            sm.nbox[tid] = nb;
             for (int j = 0; j < kept; ++j)
-                if (nms_iou(box, sm.kept_box[j]) > a.iou_thr) { alive = false; break; }
+                if (nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr) { alive = false; break; }
         }
         __syncthreads();                               // sm.box complete
         // ---- c: resolve the chunk in score order, ONE barrier per kept box: every warp publishes its ballot of live
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
             if (tid == first) {
                 sm.kept_local[nk] = first;
                 alive = false;
-            } else if (alive && nms_iou(box, sm.box[first]) > a.iou_thr) {
+            } else if (alive && nms_iou(nb, sm.nbox[first]) > a.iou_thr) {
                 alive = false;
             }
             ++nk;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
             const int i = sm.kept_local[k];
             const float4 bx = sm.box[i];
             const unsigned long long key = keys[base + i];
-            sm.kept_box[kept + k] = bx;
+            sm.kept_nbox[kept + k] = sm.nbox[i];
             reinterpret_cast<float4 *>(boxes_out)[kept + k] = bx;
             scores_out[kept + k] = __uint_as_float((unsigned)(key >> 32));
             if (a.sel_anchor)
