@@ -672,6 +672,9 @@ static int run_graphed(mpn_handle *h, const mpn_inputs *in, const mpn_params *p,
         else if (victim->exec && e.last_used < victim->last_used) victim = &e;
     }
     if (!hit) {
+        // Capturing + instantiating costs far more than eight direct launches: a caller that keeps passing new pointers
+        // (a whole cache worth of misses in a row) is served by direct launches from then on.
+        if (++h->graph_miss_streak > kGraphCache) { h->graphs_disabled = true; return 1; }
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
@@ -697,6 +700,7 @@ static int run_graphed(mpn_handle *h, const mpn_inputs *in, const mpn_params *p,
         victim->exec = exec; victim->key = key; victim->launches = n_launches;
         hit = victim;
     }
+    else h->graph_miss_streak = 0;
     hit->last_used = ++h->graph_clock;
     MPN_CUDA(h, cudaGraphLaunch(hit->exec, s));
     h->last_launches = hit->launches;

@@ -14,7 +14,7 @@ struct HostSlot {
 }  // namespace mpn
 
 namespace mpn {
-constexpr int kGraphCache = 24;
+constexpr int kGraphCache = 160;   // distinct (pointers, shapes, parameters) descriptions kept as instantiated graphs
 struct GraphKey { uint64_t v[6 + 2 * kMaxLevels + 2 + 8]; };
 struct GraphEntry {
     GraphKey key;
@@ -34,6 +34,7 @@ struct mpn_handle {
     // CUDA graphs of mpn_run, keyed by the call's pointers / shapes / parameters
     mpn::GraphEntry graphs[mpn::kGraphCache];
     uint64_t graph_clock;
+    int graph_miss_streak;  // consecutive calls that had to capture: callers that never repeat a description get direct launches
     bool cfg_use_graphs, graphs_disabled;
     unsigned debug_skip;    // mpn_debug_skip: bit i set = stage i is not launched (timing experiments only)
     // detect workspace
