@@ -382,6 +382,11 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
         mpn_destroy(h);
         return MPN_ERR_CUDA;
     }
+    if (detect_prepare() != 0) {
+        fail(nullptr, MPN_ERR_CUDA, "sort/NMS kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mpn_destroy(h);
+        return MPN_ERR_CUDA;
+    }
     if (kpdecode_prepare(h->own_stream) != 0 || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
         fail(nullptr, MPN_ERR_CUDA, "keypoint decode setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         mpn_destroy(h);
@@ -731,7 +736,11 @@ int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_
         ProfScope prof_scope(h, s);
         return enqueue_path(h, in, p, out, s, false);
     }
-    const bool capturable = s != nullptr && s != cudaStreamLegacy && h->cfg_use_graphs && !h->graphs_disabled;
+    // a caller who is capturing this stream into a graph of their own gets the plain launch sequence recorded into it
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (s != nullptr && s != cudaStreamLegacy && cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    const bool capturable = s != nullptr && s != cudaStreamLegacy && h->cfg_use_graphs && !h->graphs_disabled &&
+                            cap == cudaStreamCaptureStatusNone;
     if (capturable) {
         rc = run_graphed(h, in, p, out, s);
         if (rc <= 0) return rc;

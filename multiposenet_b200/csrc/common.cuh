@@ -77,6 +77,7 @@ inline void prof_mark(cudaStream_t s, const char *name)
 }
 
 // ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
+int detect_prepare();   // once per device (handle creation)
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
 // after_candidates (optional): event recorded on `s` between the candidate scan and the sort / NMS kernel
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates = nullptr);

@@ -165,6 +165,7 @@ struct NmsSmem {
     NmsBox kept_nbox[kMaxDetCap];              // 20 KB
     int kept_local[kChunk];                    //  2 KB: chunk-local indices kept by step d
     unsigned alive[2][kMaskWords];             // live-candidate ballots, double buffered
+    int n_kept;                                // boxes kept by the current chunk
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
@@ -180,14 +181,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
 
     if (C <= kRankSortCap) {
         for (int i = tid; i < C; i += kNmsThreads) sm.keys[i] = gkeys[i];
+        if (tid == 0 && (C & 1)) sm.keys[C] = 0ULL;    // zero pad: never greater than a real key (score bits > 0)
         __syncthreads();
         const unsigned long long k0 = tid < C ? sm.keys[tid] : 0ULL;
         const unsigned long long k1 = tid + kNmsThreads < C ? sm.keys[tid + kNmsThreads] : 0ULL;
         int r0 = 0, r1 = 0;
-        for (int j = 0; j < C; ++j) {                  // keys are distinct (they carry the anchor index)
-            const unsigned long long kj = sm.keys[j];
-            r0 += kj > k0;
-            r1 += kj > k1;
+        if (tid < C) {                                 // warps without a key skip the scan
+            // keys are distinct (they carry the anchor index); two keys per 16-byte broadcast load
+            const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sm.keys);
+            const int c2 = (C + 1) >> 1;
+#pragma unroll 4
+            for (int j = 0; j < c2; ++j) {
+                const ulonglong2 kj = k2[j];
+                r0 += (kj.x > k0) + (kj.y > k0);
+                r1 += (kj.x > k1) + (kj.y > k1);
+            }
         }
         if (tid < C) sm.sorted[r0] = k0;
         if (tid + kNmsThreads < C) sm.sorted[r1] = k1;
@@ -244,17 +252,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
             for (int j = 0; j < kept; ++j)
                 if (nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr) { alive = false; break; }
         }
-        __syncthreads();                               // sm.box complete
+        const int n_warps = (n + 31) >> 5;             // warps that hold candidates of this chunk
+        if (warp >= n_warps && lane == 0) { sm.alive[0][warp] = 0u; sm.alive[1][warp] = 0u; }
+        __syncthreads();                               // sm.box complete, idle warps' ballots zeroed
         // ---- c: resolve the chunk in score order, ONE barrier per kept box: every warp publishes its ballot of live
         //      candidates (double buffered), every thread finds the first live candidate from the 16 words, reads that
         //      candidate's box from sm.box and drops itself if it overlaps it too much; the winner records itself.
         int nk = 0;
         const int room = a.max_det - kept;
         unsigned my_word = __ballot_sync(0xffffffffu, alive);
-        for (int iter = 0; nk < room; ++iter) {
+        // only the warps that hold candidates take part (named barrier 1): fewer warps, cheaper barrier
+        for (int iter = 0; warp < n_warps && nk < room; ++iter) {
             unsigned *pub = sm.alive[iter & 1];
             if (lane == 0) pub[warp] = my_word;
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"r"(n_warps * 32) : "memory");
             const unsigned wv = lane < kMaskWords ? pub[lane] : 0u;
             const unsigned nz = __ballot_sync(0xffffffffu, wv != 0u);
             if (nz == 0u) break;                       // uniform over the CTA: nothing left alive in this chunk
@@ -269,7 +280,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
             ++nk;
             my_word = __ballot_sync(0xffffffffu, alive);
         }
-        __syncthreads();                               // sm.kept_local complete
+        if (tid == 0) sm.n_kept = nk;                  // warp 0 always takes part
+        __syncthreads();                               // sm.kept_local, sm.n_kept complete
+        nk = sm.n_kept;
         // ---- e: the kept candidates write themselves out
         for (int k = tid; k < nk; k += kNmsThreads) {
             const int i = sm.kept_local[k];
@@ -345,14 +358,15 @@ int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
     return 1;
 }
 
+// per device, at handle creation: the sort / NMS kernel needs more than the default 48 KB of dynamic shared memory
+int detect_prepare()
+{
+    const cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
-        if (e != cudaSuccess) return -(int)e;
-        attr_set = true;
-    }
     int launches = 0;
     if (a.cls) {
         const long long total = (long long)a.B * t.num_anchors;

@@ -170,6 +170,31 @@ def test_detect_nchw_levels_equal_concatenated_layout(det6):
         assert_bit_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), k)
 
 
+def test_full_path_from_raw_nchw_head_outputs(det6):
+    """the whole path fed with the raw per-level NCHW class_net / box_net outputs (the
+    reshape_and_concatenate of detector/box_predictor.py:53-90 never happens) equals the concatenated-layout result."""
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    B, n_loc = wl.batch, wl.n_loc
+    cls_levels, box_levels, off = [], [], 0
+    for s_ in wl.strides:
+        gh, gw = -(-wl.height // s_), -(-wl.width // s_)
+        n = gh * gw * n_loc
+        cls_levels.append(_cuda(inp["class_logits"][:, off:off + n].reshape(B, gh, gw, n_loc).transpose(0, 3, 1, 2)))
+        box_levels.append(_cuda(inp["encoded_boxes"][:, off:off + n].reshape(B, gh, gw, n_loc * 4).transpose(0, 3, 1, 2)))
+        off += n
+    hml = _cuda(inp["heatmap_logits"])
+    a = det6.run_device(_cuda(inp["encoded_boxes"]), _cuda(inp["class_logits"]), hml, prn_mode="bf16")
+    torch.cuda.synchronize()
+    a = {k: v.cpu().numpy().copy() for k, v in a.items()}
+    b = det6.run_device(box_levels, cls_levels, hml, (wl.height, wl.width), prn_mode="bf16")
+    torch.cuda.synchronize()
+    n = int(a["person_offsets"][-1])
+    for k, v in b.items():
+        rows = n if k in ("keypoint_scores", "keypoint_positions") else None
+        assert_bit_equal(v.cpu().numpy()[:rows], a[k][:rows], k)
+
+
 # ----------------------------------------------------------------------------------------------- heatmaps
 @pytest.mark.parametrize("key", ["tiny", "c1"])
 def test_heatmaps_bit_exact(det6, key):
