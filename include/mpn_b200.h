@@ -174,6 +174,15 @@ MPN_API int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p,
 MPN_API int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
                  float *keypoint_heatmaps, float *segmentation_masks, float *minmax, void *stream);
 
+/* SURVEY.md section 8(f) row 2, the step in front of the path: the tail of KeypointSubnet fused with mpn_heatmaps --
+ * detector/keypoint_subnet.py:49-58 (heatmaps = conv2d(x, 18, kernel_size=1) + bias, then NCHW -> NHWC) followed by
+ * create_pb.py:73-76,90,92.  features [B, 64, hh, ww] f32 NCHW (x after final_bn + ReLU), weight [64, 18] f32 (the
+ * [1,1,64,18] HWIO kernel of the layer 'heatmaps'), bias [18].  heatmap_logits [B, hh, ww, 18] is optional (NULL: the
+ * logits tensor is never materialised); the other outputs are those of mpn_heatmaps.                            */
+MPN_API int mpn_heatmap_head(mpn_handle *h, const float *features, const float *weight, const float *bias, int32_t batch,
+                             int32_t hm_height, int32_t hm_width, float *heatmap_logits, float *keypoint_heatmaps,
+                             float *segmentation_masks, float *minmax, void *stream);
+
 /* create_pb.py:90-94 + tf.image.crop_and_resize create_pb.py:106-109.  boxes [N,4], box_ind [N] i32,
  * minmax [B,K,2] or NULL (no normalisation) -> crops [N, crop_h, crop_w, K] f32                        */
 MPN_API int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,

@@ -512,6 +512,23 @@ int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int3
                     "heatmaps");
 }
 
+int mpn_heatmap_head(mpn_handle *h, const float *features, const float *weight, const float *bias, int32_t batch,
+                     int32_t hm_height, int32_t hm_width, float *heatmap_logits, float *keypoint_heatmaps,
+                     float *segmentation_masks, float *minmax, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!features || !weight || !bias || !keypoint_heatmaps) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(h, MPN_ERR_CAPACITY, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (hm_height < 1 || hm_width < 1 || (hm_height * hm_width) % 256 != 0 || hm_height * hm_width > h->max_hm_pix)
+        return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 256 within the handle's capacity");
+    if (reinterpret_cast<uintptr_t>(features) % 16 != 0 || (heatmap_logits && reinterpret_cast<uintptr_t>(heatmap_logits) % 8 != 0))
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "features must be 16-byte aligned (heatmap_logits 8-byte)");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_heatmap_head(features, weight, bias, batch, hm_height, hm_width, heatmap_logits,
+                                           keypoint_heatmaps, segmentation_masks, h->minmax_ws, minmax, h->hm_partial,
+                                           h->hm_counter, (cudaStream_t)stream), true, "heatmap head");
+}
+
 int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
              int32_t hm_width, const float *boxes, const int32_t *box_ind, int32_t n, float *crops, void *stream)
 {

@@ -85,6 +85,9 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cud
 int heatmap_chunks_per_image(int B, int hh, int ww);
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
                     float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s);
+int launch_heatmap_head(const float *x, const float *w, const float *bias, int B, int hh, int ww, float *logits, float *kh,
+                        float *seg, float *minmax_ws, float *minmax_out, int *partial_ws, unsigned int *counter_ws,
+                        cudaStream_t s);
 int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s);
 // crop of the padded (20 floats / pixel) normalised workspace written by launch_normalise
 bool crop_padded_supported(int crop_h, int crop_w);

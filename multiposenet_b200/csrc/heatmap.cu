@@ -24,6 +24,58 @@ constexpr int kNK = 17;             // keypoint channels
 constexpr int kCH = 18;             // channels of the subnet output
 constexpr int kHmThreads = 288;     // 9 warps: 288 float4 = 64 pixels x 18 channels
 constexpr int kHmPix = 64;
+constexpr int kPadCh = 20;          // channels per pixel of the padded layouts (normalised map, conv kernel rows)
+constexpr int kGroups = kPadCh / 4;
+
+// Tail of the heatmap kernels.  publish_minmax: the CTA's per-channel (min, max) in s_min / s_max go to the partial array;
+// the last CTA of the image (threadfence + counter) folds all CTAs' values into minmax[img] and re-arms the counter.
+__device__ __forceinline__ void publish_minmax(int *s_min, int *s_max, int *s_last, int *__restrict__ partial,
+                                               unsigned int *__restrict__ counter, int *__restrict__ minmax)
+{
+    const int img = blockIdx.y, tid = threadIdx.x;
+    int *my = partial + ((size_t)img * gridDim.x + blockIdx.x) * kNK * 2;
+    if (tid < kNK) { my[tid * 2] = s_min[tid]; my[tid * 2 + 1] = s_max[tid]; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_last = (atomicAdd(counter + img, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
+    __syncthreads();
+    if (tid < kNK * 8) {
+        const int c = tid % kNK, slice = tid / kNK;
+        int lo = 0x7f800000, hi = 0;
+        for (int i = slice; i < (int)gridDim.x; i += 8) {
+            const int *q = partial + ((size_t)img * gridDim.x + i) * kNK * 2 + c * 2;
+            lo = min(lo, __ldcg(q)); hi = max(hi, __ldcg(q + 1));
+        }
+        atomicMin(&s_min[c], lo); atomicMax(&s_max[c], hi);
+    }
+    __syncthreads();
+    if (tid < kNK) {
+        minmax[((size_t)img * kNK + tid) * 2] = s_min[tid];
+        minmax[((size_t)img * kNK + tid) * 2 + 1] = s_max[tid];
+    }
+    if (tid == 0) counter[img] = 0u;
+}
+
+// fold_minmax: every thread's four running (min, max) -> the CTA's, then publish.
+__device__ __forceinline__ void fold_minmax(const int (&ch)[4], const float (&mn)[4], const float (&mx)[4], int *s_min,
+                                            int *s_max, int *s_last, int *__restrict__ partial,
+                                            unsigned int *__restrict__ counter, int *__restrict__ minmax)
+{
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ch[j] < kNK) {
+            atomicMin(&s_min[ch[j]], __float_as_int(mn[j]));     // sigmoid output is >= 0: integer order == float order
+            atomicMax(&s_max[ch[j]], __float_as_int(mx[j]));
+        }
+    }
+    __syncthreads();
+    publish_minmax(s_min, s_max, s_last, partial, counter, minmax);
+}
 
 // grid = (chunks per image, B).  Thread t of a CTA always sees the four channels (4 t + j) mod 18 of its 64-pixel tiles,
 // so its running min / max live in registers.  Outputs are written straight from registers: within a warp the 17-channel
@@ -80,40 +132,105 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
             }
         }
     }
+    fold_minmax(ch, mn, mx, s_min, s_max, &s_last, partial, counter, minmax);
+}
+
+// SURVEY section 8(f) row 2 -- the tail of KeypointSubnet fused in front of the activation pass:
+//   detector/keypoint_subnet.py:49-58   heatmaps = conv2d(x, 18, kernel_size=1) + bias, NCHW -> NHWC transpose
+//   create_pb.py:73-76, 90, 92          sigmoid / split / per-(image, channel) min and max
+// x is the 64-channel NCHW feature map after final_bn + ReLU.  One thread per pixel, 256 pixels per CTA tile: the tile of
+// x is staged through shared memory 32 input channels at a time (coalesced rows of the channel planes), the [64][18]
+// kernel sits in shared memory padded to 20 columns and is read as broadcast 16-byte vectors, and every thread keeps its
+// pixel's 18 accumulators in registers: 18 fma per 6 shared-memory loads, ascending input channel.  The pixel's logits
+// are optionally stored (72 contiguous bytes), then activated and written exactly like heatmap_kernel does; the logits
+// tensor (72 B / pixel written and read back) never has to exist.
+constexpr int kHeadCin = 64;
+constexpr int kHeadPix = 256;          // pixels per tile = threads per CTA
+constexpr int kHeadChunk = 32;         // input channels staged at a time
+__global__ void __launch_bounds__(kHeadPix) heatmap_head_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                const float *__restrict__ bias, const int npix,
+                                                                const int tiles_per_img, float *__restrict__ logits,
+                                                                float *__restrict__ kh, float *__restrict__ seg,
+                                                                int *__restrict__ partial,
+                                                                unsigned int *__restrict__ counter,
+                                                                int *__restrict__ minmax)
+{
+    __shared__ __align__(16) float s_x[kHeadChunk][kHeadPix];
+    __shared__ __align__(16) float s_w[kHeadCin][kPadCh];
+    __shared__ float s_b[kCH];
+    __shared__ int s_min[kNK], s_max[kNK];
+    __shared__ int s_last;
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    float mn[kNK], mx[kNK];
+#pragma unroll
+    for (int k = 0; k < kNK; ++k) { mn[k] = __int_as_float(0x7f800000); mx[k] = 0.0f; }
+    if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
+    for (int i = tid; i < kHeadCin * kPadCh; i += kHeadPix) {
+        const int c = i / kPadCh, k = i - c * kPadCh;
+        s_w[c][k] = k < kCH ? __ldg(w + c * kCH + k) : 0.0f;
+    }
+    if (tid < kCH) s_b[tid] = __ldg(bias + tid);
+
+    const float *x_img = x + (size_t)img * kHeadCin * npix;
+    for (int tile = blockIdx.x; tile < tiles_per_img; tile += gridDim.x) {
+        const size_t pix = (size_t)tile * kHeadPix + tid;
+        float acc[kPadCh];
+        for (int half = 0; half < kHeadCin / kHeadChunk; ++half) {
+            __syncthreads();                               // previous chunk consumed (and s_w / s_b ready)
+            for (int i = tid; i < kHeadChunk * kHeadPix / 4; i += kHeadPix) {
+                const int c = i / (kHeadPix / 4), q = i - c * (kHeadPix / 4);
+                reinterpret_cast<float4 *>(&s_x[c][0])[q] = __ldcs(
+                    reinterpret_cast<const float4 *>(x_img + (size_t)(half * kHeadChunk + c) * npix + (size_t)tile * kHeadPix) + q);
+            }
+            __syncthreads();
+            if (half == 0) {
+#pragma unroll
+                for (int k = 0; k < kPadCh; ++k) acc[k] = k < kCH ? s_b[k] : 0.0f;
+            }
+#pragma unroll 4
+            for (int c = 0; c < kHeadChunk; ++c) {
+                const float xv = s_x[c][tid];
+                const float4 *wr = reinterpret_cast<const float4 *>(&s_w[half * kHeadChunk + c][0]);
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const float4 wv = wr[g];
+                    acc[4 * g + 0] = __fmaf_rn(xv, wv.x, acc[4 * g + 0]);
+                    acc[4 * g + 1] = __fmaf_rn(xv, wv.y, acc[4 * g + 1]);
+                    acc[4 * g + 2] = __fmaf_rn(xv, wv.z, acc[4 * g + 2]);
+                    acc[4 * g + 3] = __fmaf_rn(xv, wv.w, acc[4 * g + 3]);
+                }
+            }
+        }
+        if (logits) {
+            float2 *lg = reinterpret_cast<float2 *>(logits + ((size_t)img * npix + pix) * kCH);
+#pragma unroll
+            for (int k = 0; k < kCH / 2; ++k) lg[k] = make_float2(acc[2 * k], acc[2 * k + 1]);
+        }
+        float *kp = kh + ((size_t)img * npix + pix) * kNK;
+#pragma unroll
+        for (int k = 0; k < kNK; ++k) {
+            const float sg = exact_sigmoidf(acc[k]);
+            mn[k] = fminf(mn[k], sg); mx[k] = fmaxf(mx[k], sg);
+            kp[k] = sg;
+        }
+        if (seg) seg[(size_t)img * npix + pix] = acc[kNK];
+    }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (ch[j] < kNK) {
-            atomicMin(&s_min[ch[j]], __float_as_int(mn[j]));     // sigmoid output is >= 0: integer order == float order
-            atomicMax(&s_max[ch[j]], __float_as_int(mx[j]));
+    for (int k = 0; k < kNK; ++k) {
+        float lo = mn[k], hi = mx[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&s_min[k], __float_as_int(lo));
+            atomicMax(&s_max[k], __float_as_int(hi));
         }
     }
     __syncthreads();
-    int *my = partial + ((size_t)img * gridDim.x + blockIdx.x) * kNK * 2;
-    if (tid < kNK) { my[tid * 2] = s_min[tid]; my[tid * 2 + 1] = s_max[tid]; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(counter + img, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
-    __syncthreads();
-    if (tid < kNK * 16) {
-        const int c = tid % kNK, slice = tid / kNK;
-        int lo = 0x7f800000, hi = 0;
-        for (int i = slice; i < (int)gridDim.x; i += 16) {
-            const int *q = partial + ((size_t)img * gridDim.x + i) * kNK * 2 + c * 2;
-            lo = min(lo, __ldcg(q)); hi = max(hi, __ldcg(q + 1));
-        }
-        atomicMin(&s_min[c], lo); atomicMax(&s_max[c], hi);
-    }
-    __syncthreads();
-    if (tid < kNK) {
-        minmax[((size_t)img * kNK + tid) * 2] = s_min[tid];
-        minmax[((size_t)img * kNK + tid) * 2 + 1] = s_max[tid];
-    }
-    if (tid == 0) counter[img] = 0u;
+    publish_minmax(s_min, s_max, &s_last, partial, counter, minmax);
 }
 
 // create_pb.py:93-94 on one tap
@@ -128,8 +245,6 @@ __device__ __forceinline__ float normalise_tap(float v, float m, float M, float 
 // floats (80 bytes): the crop kernel then fetches a tap's channels as aligned 16-byte vectors, 5 per pixel (it is bound
 // by L1 throughput and instruction issue; scalar taps cost 4x the load instructions and wavefronts).
 // One thread per (pixel, group of 4 channels); grid = (chunks, B).
-constexpr int kPadCh = 20;
-constexpr int kGroups = kPadCh / 4;
 __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
                                                         const int npix, float *__restrict__ nh)
 {
@@ -432,6 +547,30 @@ int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *s
     prof_mark(s, "heatmap");
     heatmap_kernel<<<grid, kHmThreads, 0, s>>>(hml, npix, tiles, kh, seg, partial_ws, counter_ws,
                                                reinterpret_cast<int *>(minmax_ws));
+    ++launches;
+    if (minmax_out) {
+        const int nmm = B * kNK * 2;
+        minmax_copy_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(minmax_ws, minmax_out, nmm);
+        ++launches;
+    }
+    return launches;
+}
+
+int launch_heatmap_head(const float *x, const float *w, const float *bias, int B, int hh, int ww, float *logits, float *kh,
+                        float *seg, float *minmax_ws, float *minmax_out, int *partial_ws, unsigned int *counter_ws,
+                        cudaStream_t s)
+{
+    const int npix = hh * ww;
+    if (npix % kHeadPix != 0) return -(int)cudaErrorInvalidValue;     // true for every image that is a multiple of 128
+    const int tiles = npix / kHeadPix;
+    int launches = 0;
+    // the partial array is sized for heatmap_chunks_per_image() <= ceil(npix / 128) chunks: tiles <= that
+    int per_img = (148 * 6 + B - 1) / B;
+    if (per_img > tiles) per_img = tiles;
+    dim3 grid(per_img, B);
+    prof_mark(s, "heatmap_head");
+    heatmap_head_kernel<<<grid, kHeadPix, 0, s>>>(x, w, bias, npix, tiles, logits, kh, seg, partial_ws, counter_ws,
+                                                  reinterpret_cast<int *>(minmax_ws));
     ++launches;
     if (minmax_out) {
         const int nmm = B * kNK * 2;

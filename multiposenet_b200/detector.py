@@ -383,6 +383,21 @@ class Detector:
                                            self._stream()))
         return kh, seg, mm
 
+    def heatmap_head(self, features, weight, bias, want_logits=True):
+        """detector/keypoint_subnet.py:49-58 (1x1 conv 64 -> 18 + bias, NCHW -> NHWC) fused with heatmaps():
+        features [B,64,h,w] CUDA f32 -> (heatmap_logits [B,h,w,18] or None, keypoint_heatmaps, segmentation_masks, minmax)."""
+        B, cin, h, w = features.shape
+        if cin != 64 or tuple(weight.shape) != (64, 18) or tuple(bias.shape) != (18,):
+            raise ValueError("expected features [B,64,h,w], weight [64,18], bias [18]")
+        dev = self.device
+        lg = torch.empty((B, h, w, 18), dtype=torch.float32, device=dev) if want_logits else None
+        kh = torch.empty((B, h, w, 17), dtype=torch.float32, device=dev)
+        seg = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        mm = torch.empty((B, 17, 2), dtype=torch.float32, device=dev)
+        self._check(self._lib.mpn_heatmap_head(self._handle, _ptr(features), _ptr(weight), _ptr(bias), B, h, w, _ptr(lg),
+                                               _ptr(kh), _ptr(seg), _ptr(mm), self._stream()))
+        return lg, kh, seg, mm
+
     def crop(self, keypoint_heatmaps, boxes, box_ind, minmax=None):
         """create_pb.py:90-94,106-109 -> crops [N,56,36,17]."""
         B, h, w, _ = keypoint_heatmaps.shape

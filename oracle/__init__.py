@@ -165,6 +165,17 @@ def heatmaps(hml, nk=NUM_KEYPOINTS):
     return kh, seg, mn, mx
 
 
+def heatmap_head(features, weight, bias):
+    """SURVEY section 8(f) row 2 -- detector/keypoint_subnet.py:49-58: tf.layers.conv2d(x, 18, kernel_size=1) with bias on
+    the NCHW feature map, then the NCHW -> NHWC transpose (:56).  features [B,64,h,w], weight [64,18] (the [1,1,64,18]
+    HWIO kernel), bias [18] -> heatmap logits [B,h,w,18] float32 (accumulated in float64: the order of TF's own
+    convolution kernel is unspecified, parity is held to 1e-4)."""
+    x = np.asarray(features, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64)
+    out = np.einsum("bchw,ck->bhwk", x, w) + np.asarray(bias, dtype=np.float64)
+    return out.astype(np.float32)
+
+
 def crop_and_resize(img, boxes, box_ind, crop_size=CROP_SIZE, mn=None, mx=None):
     """tf.image.crop_and_resize (create_pb.py:106-109); with mn/mx the taps are min-max
     normalised first (create_pb.py:90-94).  img [B,h,w,c] -> [N,ch,cw,c]."""

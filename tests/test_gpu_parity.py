@@ -209,6 +209,32 @@ def test_heatmaps_bit_exact(det6, key):
     assert_bit_equal(gmm[..., 1], mx, "max")
 
 
+def test_heatmap_head_fused_with_activation(det6):
+    """1x1 conv (64 -> 18) + bias + NCHW -> NHWC fused in front of sigmoid / split / min-max.
+    Logits within 1e-4 of the float64 oracle; everything downstream bit-identical to running the un-fused heatmap
+    stage on the kernel's own logits."""
+    rng = np.random.default_rng(12)
+    B, h, w = 2, 64, 64
+    x = np.maximum(rng.standard_normal((B, 64, h, w)), 0).astype(np.float32)             # after final_bn + ReLU
+    wt = (rng.standard_normal((64, 18)) * 0.4).astype(np.float32)
+    bias = np.concatenate([np.full(17, -4.59511985, np.float32), np.zeros(1, np.float32)])   # keypoint_subnet.py:41-47
+    lg, kh, seg, mm = det6.heatmap_head(_cuda(x), _cuda(wt), _cuda(bias))
+    want = oracle.heatmap_head(x, wt, bias)
+    np.testing.assert_allclose(lg.cpu().numpy(), want, rtol=RTOL_FP32, atol=RTOL_FP32 * np.abs(want).max())
+    kh2, seg2, mm2 = det6.heatmaps(lg)
+    assert_bit_equal(kh.cpu().numpy(), kh2.cpu().numpy(), "keypoint_heatmaps")
+    assert_bit_equal(seg.cpu().numpy(), seg2.cpu().numpy(), "segmentation_masks")
+    assert_bit_equal(mm.cpu().numpy(), mm2.cpu().numpy(), "min / max")
+    okh, oseg, omn, omx = oracle.heatmaps(want)
+    np.testing.assert_allclose(kh.cpu().numpy(), okh, rtol=RTOL_FP32, atol=1e-7)
+    np.testing.assert_allclose(mm.cpu().numpy()[..., 1], omx, rtol=RTOL_FP32)
+    # without the logits output (the tensor is never materialised) the other outputs are unchanged
+    lg3, kh3, seg3, mm3 = det6.heatmap_head(_cuda(x), _cuda(wt), _cuda(bias), want_logits=False)
+    assert lg3 is None
+    assert_bit_equal(kh3.cpu().numpy(), kh.cpu().numpy(), "keypoint_heatmaps without logits")
+    assert_bit_equal(mm3.cpu().numpy(), mm.cpu().numpy(), "min / max without logits")
+
+
 # ----------------------------------------------------------------------------------------------- crop_and_resize
 def test_crop_and_resize_bit_exact(det6):
     wl = synthetic.WORKLOADS["tiny"]

@@ -269,6 +269,22 @@ def test_keypoint_decode_random_vs_spec():
     assert (gap > 0).all()
 
 
+def test_heatmap_head_known_answers():
+    """keypoint_subnet.py:49-58: a 1x1 convolution is a per-pixel matrix product; checked against torch's conv2d."""
+    import torch
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 64, 8, 16)).astype(f32)
+    w = (rng.standard_normal((64, 18)) * 0.1).astype(f32)
+    b = rng.standard_normal(18).astype(f32)
+    got = oracle.heatmap_head(x, w, b)
+    assert got.shape == (2, 8, 16, 18)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w.T.copy()).double()[:, :, None, None],
+                                     torch.from_numpy(b).double()).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-6)
+    one = oracle.heatmap_head(np.ones((1, 64, 4, 16), f32), np.full((64, 18), 0.5, f32), np.zeros(18, f32))
+    assert np.all(one == 32.0)
+
+
 # ---------------------------------------------------------------------------- (8) get_keypoints: GOLDEN (reference output)
 def test_get_keypoints_golden_vectors_from_reference():
     g = np.load(os.path.join(HERE, "golden", "get_keypoints.npz"))
