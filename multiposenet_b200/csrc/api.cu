@@ -15,6 +15,7 @@ using namespace mpn;
 
 namespace mpn {
 thread_local Profiler *g_prof = nullptr;
+thread_local int g_pdl = 0;
 }
 
 
@@ -377,6 +378,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cand, cudaEventDisableTiming);
     h->cfg_use_graphs = getenv("MPN_NO_GRAPH") == nullptr;
+    h->use_pdl = getenv("MPN_NO_PDL") == nullptr;
     if (e != cudaSuccess) {
         fail(nullptr, MPN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
         mpn_destroy(h);
@@ -603,6 +605,11 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
 {
     cudaStream_t sd = fork ? h->aux_stream : s;     // detect branch
     cudaStream_t sa = s;                            // heatmap branch
+    // programmatic dependent launch along each branch (common.cuh); off while per-kernel events are being recorded
+    struct PdlScope {
+        PdlScope(int on) { g_pdl = on; }
+        ~PdlScope() { g_pdl = 0; }
+    } pdl_scope(h->use_pdl && !h->prof.on ? 1 : 0);
     if (fork) {
         MPN_CUDA(h, cudaEventRecord(h->ev_fork, s));
         MPN_CUDA(h, cudaStreamWaitEvent(sd, h->ev_fork, 0));

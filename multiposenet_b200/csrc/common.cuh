@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/mpn_b200.h"
 
@@ -75,6 +76,32 @@ inline void prof_mark(cudaStream_t s, const char *name)
         p->name[p->n++] = name;
     }
 }
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// Every kernel of the path starts with pdl_trigger() + pdl_wait() (prn_fused_kernel waits later, after its prologue and
+// its first weight loads): launched with the programmatic-serialization attribute, the CTAs of kernel N+1 are placed and
+// run their prologue while the last wave of kernel N drains, and block in griddepcontrol.wait until kernel N has
+// completed and flushed.  Because EVERY kernel waits before it exits, completion is transitive along a stream.  Without
+// the attribute both instructions are no-ops.  g_pdl is set by api.cu around the enqueue of one call.
+extern thread_local int g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                            Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
 int detect_prepare();   // once per device (handle creation)

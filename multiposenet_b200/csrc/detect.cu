@@ -93,6 +93,7 @@ __global__ void anchors_kernel(const AnchorTable t, float4 *out)
 __global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a, const int A, const long long total,
                                                               const int vec_ok)
 {
+    pdl_trigger();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long e0 = t * 4;
     if (e0 >= total) return;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a
 // Per-level NCHW logits [B, n_loc, gh, gw]: threads walk memory order, anchor index = off + (y*gw+x)*n_loc + k.
 __global__ void __launch_bounds__(256) candidates_nchw_kernel(const AnchorTable t, const DetectArgs a)
 {
+    pdl_trigger();
     const int img = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;   // position inside the image's concatenated levels
     if (e >= t.num_anchors) return;
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &sm = *reinterpret_cast<NmsSmem *>(smem_raw);
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();                                        // the candidate scan has completed
     const int C = min(a.cand_count[img], a.key_cap);
     unsigned long long *gkeys = a.cand_keys + (size_t)img * a.key_cap;
     const unsigned long long *keys;
@@ -315,6 +319,8 @@ __global__ void __launch_bounds__(256) person_list_kernel(const DetectArgs a)
 {
     __shared__ int s_off[1025];
     const int tid = threadIdx.x, lane = tid & 31;
+    pdl_trigger();
+    pdl_wait();                                        // sort / NMS has completed
     if (tid < 32) {
         int running = 0;
         for (int b0 = 0; b0 < a.B; b0 += 32) {
@@ -382,11 +388,11 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cud
     ++launches;
     if (after_candidates) cudaEventRecord(after_candidates, s);
     prof_mark(s, "sort_nms");
-    sort_nms_kernel<<<a.B, kNmsThreads, sizeof(NmsSmem), s>>>(t, a);
+    launch_k(sort_nms_kernel, dim3(a.B), dim3(kNmsThreads), sizeof(NmsSmem), s, true, t, a);
     ++launches;
     if (a.person_box) {
         prof_mark(s, "person_list");
-        person_list_kernel<<<1, 256, 0, s>>>(a);
+        launch_k(person_list_kernel, dim3(1), dim3(256), 0, s, true, a);
         ++launches;
     }
     return launches;

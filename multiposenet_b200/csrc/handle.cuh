@@ -36,6 +36,7 @@ struct mpn_handle {
     uint64_t graph_clock;
     int graph_miss_streak;  // consecutive calls that had to capture: callers that never repeat a description get direct launches
     bool cfg_use_graphs, graphs_disabled;
+    bool use_pdl;           // programmatic dependent launch between consecutive kernels of a branch
     unsigned debug_skip;    // mpn_debug_skip: bit i set = stage i is not launched (timing experiments only)
     // detect workspace
     unsigned long long *cand_keys;

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
     __shared__ int s_min[kNK], s_max[kNK];
     __shared__ int s_last;
     const int img = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
     // Straight-line inner code: every element gets the sigmoid (1 in 18 is the mask channel and keeps its raw value by a
     // select), every element has ONE precomputed destination (its keypoint_heatmaps slot, or its segmentation_masks slot),
     // and the mask channel's min / max registers are simply never merged.  No divergence inside a warp.
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kHeadPix) heatmap_head_kernel(const float *__r
                                                                 unsigned int *__restrict__ counter,
                                                                 int *__restrict__ minmax)
 {
+    pdl_trigger();
     __shared__ __align__(16) float s_x[kHeadChunk][kHeadPix];
     __shared__ __align__(16) float s_w[kHeadCin][kPadCh];
     __shared__ float s_b[kCH];
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict_
 {
     __shared__ float s_m[kPadCh], s_d[kPadCh], s_mask[kPadCh];
     const int img = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();                                        // the heatmap kernel (min / max fold included) has completed
     if (threadIdx.x < kPadCh) {
         const bool real = threadIdx.x < kNK;
         const float m = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2) : 0.0f;
@@ -295,6 +299,8 @@ __global__ void __launch_bounds__(256) crop_padded_kernel(const float *__restric
     __shared__ PixTabP s_tab[kCropPMaxPix];
     __shared__ __align__(16) float s_out[kCropPMaxPix * kNK];
     const int n = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();                                        // normalised map and person list are complete
     const int N = n_dev ? *n_dev : n_host;
     if (n >= N) return;
     const int rows_per_band = (crop_h + gridDim.y - 1) / gridDim.y;
@@ -397,6 +403,8 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
 {
     __shared__ PixTab s_tab[kCropMaxPix];
     __shared__ float s_m[kNK], s_M[kNK], s_mask[kNK];
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x;
     const int N = n_dev ? *n_dev : n_host;
     if (n >= N) return;
@@ -526,14 +534,25 @@ __global__ void minmax_copy_kernel(const float *ws, float *out, int n)
 
 int heatmap_chunks_per_image(int B, int hh, int ww)
 {
-    // Two 64-pixel tiles per trip.  Small calls: one trip per CTA (every load of the kernel is issued in the first few
-    // hundred cycles of a CTA's life, many resident CTAs hide the HBM latency).  Large calls: about six CTAs per SM, each
-    // making a whole number of trips, so that the per-thread set-up (channel pattern, destinations) is amortised.
+    // Two 64-pixel tiles per trip, and at most ONE resident wave of CTAs: 4 CTAs of 288 threads fit an SM (registers), and
+    // a grid of 1.35 or 1.5 waves costs two full rounds of trips (measured: 800 CTAs x 2 trips at 640x640x8 took as long
+    // as 4 trips).  The wave leaves room for the B single-CTA sort / NMS blocks that run beside this kernel (an SM that
+    // holds one of them still takes two heatmap CTAs).  Small calls end up with one trip per CTA.
+    static int slots = 0;
+    if (slots == 0) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heatmap_kernel, kHmThreads, 0) != cudaSuccess) per_sm = 0;
+        cudaGetLastError();
+        slots = per_sm > 0 && sms > 0 ? per_sm * sms : 4 * 148;
+    }
     const int tiles = (hh * ww + kHmPix - 1) / kHmPix;
-    const long long pairs = ((long long)tiles * B + 1) / 2;
-    long long trips = (pairs + 148 * 6 / 2) / (148 * 6);
-    if (trips < 1) trips = 1;
-    const int per_img = (int)((tiles + 2 * trips - 1) / (2 * trips));
+    int budget = slots - 2 * (B < 148 ? B : 148);
+    int cap = budget / B;
+    if (cap < 1) cap = 1;
+    const int trips = (tiles + 2 * cap - 1) / (2 * cap);
+    const int per_img = (tiles + 2 * trips - 1) / (2 * trips);
     return per_img < 1 ? 1 : per_img;
 }
 
@@ -587,7 +606,7 @@ int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww
     const int max_blocks = (total + 255) / 256;
     if (per_img > max_blocks) per_img = max_blocks;
     prof_mark(s, "normalise");
-    normalise_kernel<<<dim3(per_img, B), 256, 0, s>>>(kh, minmax, hh * ww, nh);
+    launch_k(normalise_kernel, dim3(per_img, B), dim3(256), 0, s, true, kh, minmax, hh * ww, nh);
     return 1;
 }
 
@@ -604,8 +623,8 @@ int launch_crop(const float *src, const float *minmax, int hh, int ww, const flo
         return -(int)cudaErrorInvalidValue;
     dim3 grid(n_max, bands);
     prof_mark(s, "crop");
-    crop_kernel<<<grid, 256, 0, s>>>(src, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32,
-                                     crops_bf16);
+    launch_k(crop_kernel, grid, dim3(256), 0, s, true, src, minmax, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w,
+             crops_f32, crops_bf16);
     return 1;
 }
 
@@ -622,7 +641,8 @@ int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, cons
     if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
     dim3 grid(n_max, kCropPBands);
     prof_mark(s, "crop");
-    crop_padded_kernel<<<grid, 256, 0, s>>>(nh, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w, crops_f32, crops_bf16);
+    launch_k(crop_padded_kernel, grid, dim3(256), 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w,
+             crops_f32, crops_bf16);
     return 1;
 }
 

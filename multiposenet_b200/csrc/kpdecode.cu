@@ -77,6 +77,8 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
     __shared__ float s_gmax[kNK];
     const int n = blockIdx.x / kCluster;
     const unsigned rank = cluster_rank();
+    pdl_trigger();
+    pdl_wait();                           // the PRN has completed
     const int N = n_dev ? *n_dev : n_host;
     if (n >= N) return;                   // uniform over the cluster
     const int P = crop_h * crop_w;
@@ -165,8 +167,8 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
     if (n_max <= 0) return 0;
     if (crop_h * crop_w > kMaxPerThread * kLanes * kCluster) return -(int)cudaErrorInvalidValue;
     prof_mark(s, "keypoint_decode");
-    keypoint_decode_kernel<<<n_max * kCluster, kThreads, 0, s>>>(logits, n_dev, n_host, crop_h, crop_w, scores, positions,
-                                                                argmax);
+    launch_k(keypoint_decode_kernel, dim3(n_max * kCluster), dim3(kThreads), 0, s, true, logits, n_dev, n_host, crop_h, crop_w,
+             scores, positions, argmax);
     return 1;
 }
 

@@ -19,11 +19,13 @@
 //
 // Roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) + TMEM allocation, warps 2..9 =
 // epilogue / reduce (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
-// Activations are fetched as 32-row TMA boxes, only as many as there are persons (M is fixed at 128 per MMA but
+// Activations are fetched as 16-row TMA boxes, only as many as there are persons (M is fixed at 128 per MMA but
 // rows past the last box are never loaded; their accumulator rows are garbage and never stored).
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "handle.cuh"
@@ -37,12 +39,13 @@ using namespace tc;
 
 constexpr int kHq = 4;                                   // hidden quarters of fc1
 constexpr int kFc1N = 256, kFc2N = 240;                  // UMMA N of the two layers
-constexpr int kXBox = 32;                                // rows per activation TMA box
+constexpr int kXBox = 16;                                // rows per activation TMA box (persons are padded to 16)
 constexpr int kXBoxBytes = kXBox * 128;
 constexpr int kXTileBytes = 128 * 128;                   // one 128-row activation tile (16 KB)
 constexpr int kWTileBytes = 256 * 128;                   // one weight tile (32 KB; fc2 uses 240 of the 256 rows)
 constexpr int kRingBytes = 192 * 1024;                   // stage = [W tile | X tile 0 | X tile 1 (only for > 128 persons)]
 constexpr int kMaxStages = 4;                            //   <= 128 persons: 4 stages of 48 KB, else 3 stages of 64 KB
+constexpr int kEarly = 3;                                // W1 boxes requested before the person count is known
 constexpr int kEpiWarps = 16;                           // 4 per TMEM lane quadrant: the epilogues are issue-latency bound
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 32 x 16 fp32 transpose buffers
@@ -86,6 +89,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 // 2 * grid arrivals, so the counter value at kernel entry, rounded down to a multiple of 2 * grid, is this launch's base
 // (no CTA can see more than grid - 1 arrivals of barrier 1 before it has arrived itself).  All CTAs are co-resident
 // (cooperative launch).  One thread per CTA arrives; one round trip to L2 to arrive, one to observe.
+// (A two-level version -- arrivals on per-group lines, last arrival of a group on a top counter, waiters polling a
+// separate epoch word -- was measured: its three dependent fence + atomic hops cost 3.2 and 4.0 us per barrier against
+// 1.4 and 2.1 us for this one.)
 __device__ __forceinline__ void grid_arrive(unsigned long long *arrivals)
 {
     // Called by ONE thread after a CTA-wide bar.sync: the barrier orders the other threads' stores before this
@@ -119,6 +125,14 @@ __device__ __forceinline__ void stamp(const FusedArgs &a, int slot)
     }
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)     // no arrival: the arrive comes later
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -127,14 +141,10 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  const FusedArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
-    const int N = args.n_dev ? *args.n_dev : args.n_host;
-    if (N <= 0 || N > kPrnFusedMaxRows) return;      // uniform over the grid; the general kernels take N > 256
-    const int nm = (N + 127) >> 7;                   // 128-row M tiles
-    const int nb = (N + kXBox - 1) / kXBox;          // 32-row activation boxes
+    pdl_trigger();
     const int G = gridDim.x, c = blockIdx.x;
+    // this launch's barrier base; read before this CTA can possibly have arrived anywhere
     const unsigned long long bar_base = (ld_acquire_u64(args.arrivals) / (2ull * G)) * (2ull * G);
-    const int stage_bytes = kWTileBytes + nm * kXTileBytes;
-    const int n_stages = kRingBytes / stage_bytes;   // 4 or 3
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kBarOffset);
@@ -166,25 +176,59 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int hq = c % kHq, z = c / kHq;
     const int kb0 = has_fc1 ? (int)(((long long)z * args.nkb1) / args.splits) : 0;
     const int kb1 = has_fc1 ? (int)(((long long)(z + 1) * args.nkb1) / args.splits) : 0;
+
+    // Everything above, and the first weight tiles, do not depend on the crops: under programmatic dependent launch
+    // they overlap the tail of the crop kernel.  Weight slot st sits at st * 32 KB in both ring layouts, so the first
+    // kEarly W1 boxes can be requested before the person count (and with it the layout) is known; their barriers get the
+    // transaction bytes now and the producer's arrival (with the activation bytes) after the wait.
+    int early = 0;
+    if (threadIdx.x == 0 && has_fc1) {
+        early = min(kEarly, kb1 - kb0);
+        for (int i = 0; i < early; ++i) {
+            mbar_expect_tx(full_bar + i, kFc1N * 128);
+            tma_load_2d(smem + i * kWTileBytes, &tmap_w1, full_bar + i, (kb0 + i) * BLOCK_K, hq * kFc1N, kEvictFirst);
+        }
+    }
+    pdl_wait();                                                             // crops and person count are complete
+    if (threadIdx.x == 0) stamp(args, 7);
+    const int N = args.n_dev ? *args.n_dev : args.n_host;
+    const bool run = N > 0 && N <= kPrnFusedMaxRows;   // uniform over the grid; the general kernels take N > 256
+    const int nm = (N + 127) >> 7;                   // 128-row M tiles
+    const int nb = (N + kXBox - 1) / kXBox;          // 16-row activation boxes
+    // ring: <= 128 persons: 4 stages, W slots [0, 128 KB), X slots of 16 KB behind them; else 3 stages, W slots
+    // [0, 96 KB), X slots of 32 KB behind them
+    const int n_stages = nm == 1 ? 4 : 3;
+    const int x_base = n_stages * kWTileBytes, x_stride = nm * kXTileBytes;
     const uint32_t x_bytes = (uint32_t)nb * kXBoxBytes;
+    if (!run) {
+        if (threadIdx.x == 0)
+            for (int i = 0; i < early; ++i) { mbar_arrive(full_bar + i); mbar_wait(full_bar + i, 0); }   // drain
+    } else
 
     if (warp == 0) {
         if (lane == 0) {   // ================= TMA producer =================
             int it = 0;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int st = it % n_stages;
-                mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
-                uint8_t *stage = smem + st * stage_bytes;
-                tma_load_2d(stage, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
+                uint8_t *xs = smem + x_base + st * x_stride;
+                if (it < early) {       // W box already in flight
+                    mbar_arrive_expect_tx(full_bar + st, x_bytes);
+                } else {
+                    mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
+                    tma_load_2d(smem + st * kWTileBytes, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
+                }
                 for (int b = 0; b < nb; ++b)
-                    tma_load_2d(stage + kWTileBytes + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
+                    tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
             }
             stamp(args, 1);                                                 // all fc1 loads issued
-            // (An L2 prefetch of the whole W2 tile at this point was measured: phase 3 got 2 us shorter but the two grid
-            // barriers 2 us longer -- the prefetch traffic delays the partial-sum stores and the barrier atomics -- so
-            // the run-ahead is limited to the shared-memory ring.)
-            // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces
+            // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces.
+            // Measured and not kept (profiles/r01e_summary.md): TMA L2 prefetches of the rest of the W2 tile issued here
+            // or after barrier 1, a sliding L2 prefetch window ahead of the ring in both layers, an L2 prefetch of W1
+            // from a kernel in the front half of the call, and a per-CTA rotation of the k order.  With W2 L2-resident
+            // phase 3 got only 1.1 us shorter: both streaming phases move ~97 MB (70 MB of weights + the activation
+            // boxes every CTA re-reads) from L2 to the SMs, which is ~8 us at the ~12 TB/s the L2 can deliver --
+            // they are bound by L2 -> SM bandwidth as much as by HBM.
             const int first2 = it;
             int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
             bool y1_ready = false;
@@ -197,7 +241,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         stamp(args, 6);                                     // producer saw barrier 2
                         y1_ready = true;
                         for (; flushed < it; ++flushed) {      // only ever the first n_stages k blocks of the first tile
-                            uint8_t *stg = smem + (flushed % n_stages) * stage_bytes + kWTileBytes;
+                            uint8_t *stg = smem + x_base + (flushed % n_stages) * x_stride;
                             for (int b = 0; b < nb; ++b)
                                 tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
                                             (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
@@ -205,11 +249,11 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc2N * 128);
-                    uint8_t *stage = smem + st * stage_bytes;
-                    tma_load_2d(stage, &tmap_w2, full_bar + st, kb * BLOCK_K, tile * kFc2N, kEvictFirst);
+                    uint8_t *xs = smem + x_base + st * x_stride;
+                    tma_load_2d(smem + st * kWTileBytes, &tmap_w2, full_bar + st, kb * BLOCK_K, tile * kFc2N, kEvictFirst);
                     if (y1_ready) {
                         for (int b = 0; b < nb; ++b)
-                            tma_load_2d(stage + kWTileBytes + b * kXBoxBytes, &tmap_y1, full_bar + st, kb * BLOCK_K, b * kXBox,
+                            tma_load_2d(xs + b * kXBoxBytes, &tmap_y1, full_bar + st, kb * BLOCK_K, b * kXBox,
                                         kEvictLast);
                         flushed = it + 1;
                     }
@@ -220,7 +264,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 asm volatile("fence.proxy.async;" ::: "memory");
                 stamp(args, 6);
                 for (; flushed < it; ++flushed) {
-                    uint8_t *stg = smem + (flushed % n_stages) * stage_bytes + kWTileBytes;
+                    uint8_t *stg = smem + x_base + (flushed % n_stages) * x_stride;
                     for (int b = 0; b < nb; ++b)
                         tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
                                     (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
@@ -238,10 +282,10 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int st = it % n_stages;
                     mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
                     tc_fence_after();
-                    const uint32_t s_addr = smem_u32(smem + st * stage_bytes);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(s_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + st * kWTileBytes));
+                    const uint32_t x_addr = smem_u32(smem + x_base + st * x_stride);
                     for (int m = 0; m < nm; ++m) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(s_addr + kWTileBytes + m * kXTileBytes);
+                        const uint64_t adesc = make_kmajor_sw128_desc(x_addr + m * kXTileBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
@@ -262,10 +306,10 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int st = it % n_stages;
                     mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
                     tc_fence_after();
-                    const uint32_t s_addr = smem_u32(smem + st * stage_bytes);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(s_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + st * kWTileBytes));
+                    const uint32_t x_addr = smem_u32(smem + x_base + st * x_stride);
                     for (int m = 0; m < nm; ++m) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(s_addr + kWTileBytes + m * kXTileBytes);
+                        const uint64_t adesc = make_kmajor_sw128_desc(x_addr + m * kXTileBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
@@ -557,10 +601,22 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
     a.b1 = h->b1; a.y1 = h->prn_ws.y1_bf16; a.b2 = h->b2; a.x = x_f32; a.logits = logits;
     a.arrivals = st->bar;
     a.trace = st->trace;
-    void *params[] = {&st->maps.x, &st->maps.w1, &st->maps.y1, &st->maps.w2, &a};
     prof_mark(s, "prn_fused");
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(prn_fused_kernel), dim3(st->grid),
-                                                dim3(kThreads), params, (size_t)kSmemBytes, s);
+    // Cooperative launch (co-residency of the grid is checked by the driver).  With programmatic dependent launch the
+    // CTAs become resident one by one while the crop kernel drains, which is safe for the grid barrier because the crop
+    // kernel never waits for this one and nothing else runs at that point of the call.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(st->grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)kSmemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na;
+    if (g_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, prn_fused_kernel, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2, a);
     if (e != cudaSuccess) return -(int)e;
     return 1;
 }
