@@ -144,6 +144,47 @@ __device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectAr
     return make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane), __ldg(p + 3 * plane));
 }
 
+// Flat person list in image order (create_pb.py:96-103): person_offsets = exclusive scan of num_boxes, and for every
+// person row its box and image.  Run by the LAST CTA of sort_nms_kernel to finish (one launch less on the critical
+// chain of the call); s_off is that CTA's sort area, free by then.
+__device__ __forceinline__ void person_list(const DetectArgs &a, int *s_off)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        int running = 0;
+        for (int b0 = 0; b0 < a.B; b0 += 32) {
+            const int b = b0 + lane;
+            const int n = (b < a.B) ? __ldcg(a.num_boxes + b) : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < a.B) {
+                const int off = running + incl - n;
+                if (b < 1024) s_off[b] = off;
+                a.person_offsets[b] = off;
+                if (a.person_offsets_out) a.person_offsets_out[b] = off;
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            a.person_offsets[a.B] = running;
+            if (a.person_offsets_out) a.person_offsets_out[a.B] = running;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < a.B * a.max_det; idx += blockDim.x) {
+        const int b = idx / a.max_det, k = idx - b * a.max_det;
+        if (k < __ldcg(a.num_boxes + b)) {
+            const int row = (b < 1024 ? s_off[b] : a.person_offsets[b]) + k;
+            reinterpret_cast<float4 *>(a.person_box)[row] = __ldcg(reinterpret_cast<const float4 *>(a.boxes) + idx);
+            a.person_img[row] = b;
+        }
+    }
+}
+
 // One CTA per image.
 //   1. candidate keys -> descending order (= score desc, anchor asc).  <= 1024 candidates: rank sort in shared memory
 //      (every key counts the keys above it; no barriers); more: bitonic sort, in shared memory up to 8192 keys and in the
@@ -311,47 +352,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTa
         a.num_boxes[img] = kept;
         if (a.n_candidates) a.n_candidates[img] = C;
     }
-}
-
-// Flat person list in image order (create_pb.py:96-103): person_offsets = exclusive scan of num_boxes, and for every
-// person row its box and image.  One small CTA; runs after sort_nms_kernel.
-__global__ void __launch_bounds__(256) person_list_kernel(const DetectArgs a)
-{
-    __shared__ int s_off[1025];
-    const int tid = threadIdx.x, lane = tid & 31;
-    pdl_trigger();
-    pdl_wait();                                        // sort / NMS has completed
-    if (tid < 32) {
-        int running = 0;
-        for (int b0 = 0; b0 < a.B; b0 += 32) {
-            const int b = b0 + lane;
-            const int n = (b < a.B) ? a.num_boxes[b] : 0;
-            int incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (b < a.B) {
-                const int off = running + incl - n;
-                if (b < 1024) s_off[b] = off;
-                a.person_offsets[b] = off;
-                if (a.person_offsets_out) a.person_offsets_out[b] = off;
-            }
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) {
-            a.person_offsets[a.B] = running;
-            if (a.person_offsets_out) a.person_offsets_out[a.B] = running;
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < a.B * a.max_det; idx += blockDim.x) {
-        const int b = idx / a.max_det, k = idx - b * a.max_det;
-        if (k < a.num_boxes[b]) {
-            const int row = (b < 1024 ? s_off[b] : a.person_offsets[b]) + k;
-            reinterpret_cast<float4 *>(a.person_box)[row] = reinterpret_cast<const float4 *>(a.boxes)[idx];
-            a.person_img[row] = b;
+    if (a.person_box) {                                // the last CTA to get here builds the flat person list
+        __threadfence();                               // this CTA's boxes / num_boxes are visible GPU-wide ...
+        __syncthreads();
+        if (tid == 0) sm.n_kept = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1u);
+        __syncthreads();
+        if (sm.n_kept) {
+            __threadfence();                           // ... and so are everybody else's
+            if (tid == 0) *a.done_counter = 0u;        // re-armed for the next call
+            person_list(a, reinterpret_cast<int *>(sm.keys));
         }
     }
 }
@@ -390,11 +399,6 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cud
     prof_mark(s, "sort_nms");
     launch_k(sort_nms_kernel, dim3(a.B), dim3(kNmsThreads), sizeof(NmsSmem), s, true, t, a);
     ++launches;
-    if (a.person_box) {
-        prof_mark(s, "person_list");
-        launch_k(person_list_kernel, dim3(1), dim3(256), 0, s, true, a);
-        ++launches;
-    }
     return launches;
 }
 

@@ -4,19 +4,35 @@
 // (tf.nn.softmax(axis=1): p = exp(l - max) * (1 / sum)), keypoint_scores = max p, keypoint_positions =
 // (argmax // 36 / 56, argmax % 36 / 36) with tf.argmax's first-index tie rule.
 //
-// One thread-block CLUSTER of 4 CTAs per person, each CTA of 17 x 32 threads owning a quarter of the 2016 positions
-// (a contiguous 34 KB slab of the person's logit row, read exactly once, fully coalesced; 16 values per thread stay in
-// registers for the second pass).  The per-channel maxima, exp-sums and first-argmax candidates of the four CTAs are
-// combined through distributed shared memory (two cluster barriers); softmax probabilities are never written.
+// One thread-block CLUSTER of 4 CTAs per person, each CTA of 17 x 32 threads owning a quarter of the 2016 positions (a
+// contiguous 34 KB slab of the person's logit row, read exactly once, fully coalesced; thread (channel c, lane q) sees
+// positions q, q + 32, ...: 16 values).
 //
 // argmax rule, bit-matched to the oracle without depending on the summation order of the denominator:
-// p[i] = e[i] * r with r = 1/sum and e[i] = exp(l[i] - lmax) <= 1.  e[i] * r == r iff e[i] == 1.0f (for e[i] <= 1 - 2^-24
-// the product is at least half an ulp below r and rounds to a smaller float), so the first index with maximal
-// probability is the first index whose e[i] is exactly 1.0f.  The exp recipe is monotone near 0, so "exp(d) == 1.0f"
-// is the comparison d >= x0 with x0 the most negative float whose recipe value is 1.0f (found once per device by
-// bisection with the recipe itself, kpdecode_prepare): the decision costs one subtraction and one compare per logit.
-// keypoint_scores = 1 / sum is only held to 1e-4, so the 2016-term sum uses the hardware ex2 approximation (~2 ulp per
-// term) instead of the 20-instruction exact recipe -- the kernel was instruction-issue bound on it.
+// p[i] = e[i] * r with r = 1/sum and e[i] = exp(l[i] - G) <= 1, G the channel's maximum.  e[i] * r == r iff e[i] == 1.0f
+// (for e[i] <= 1 - 2^-24 the product is at least half an ulp below r and rounds to a smaller float), so the first index
+// with maximal probability is the first index whose e[i] is exactly 1.0f.  The exp recipe is monotone near 0, so
+// "exp(d) == 1.0f" is the comparison d >= x0 with x0 the most negative float whose recipe value is 1.0f (found once per
+// device by bisection with the recipe itself, kpdecode_prepare).
+//
+// ONE pass, ONE block barrier and ONE cluster barrier per person (an earlier version took the maximum first -- block
+// reduce, cluster barrier -- then the sum -- block reduce, cluster barrier -- then a third cluster barrier to keep the
+// peers alive: a serial chain of ~5 us per person that left HBM idle, 1.8 TB/s at 2801 persons).  Every thread folds its
+// 16 values into a partial (m, s = sum exp(l - m), f = first position with l - m >= x0); partials merge like an online
+// softmax: M = max m, S = sum s * exp(m - M), F = min f over the partials with m == M.  A partial with m < M can still
+// hold positions that satisfy the GLOBAL rule l - M >= x0 when m - M >= x0 (two different floats within half an ulp of
+// 1.0 of each other: only possible for |M| < 0.5); its own f was taken against m, not M, so such a "near tie" is only
+// flagged and the flagged channel is rescanned exactly against M by CTA 0 (never seen on real logits, covered by a
+// test).  keypoint_scores = 1 / S is held to 1e-4 only, so the terms use the hardware ex2 approximation.
+//
+// The peers write their per-channel partials straight into CTA 0's shared memory (distributed shared memory), then the
+// cluster barrier, then CTA 0 merges and stores.  Two kernels share this arithmetic: keypoint_decode_kernel, one cluster
+// per person with the logits loaded straight into registers (lowest latency, few persons), and
+// keypoint_decode_stream_kernel, PERSISTENT clusters that walk the persons with every CTA's slab arriving by one bulk
+// copy (TMA) into a three-slot shared-memory ring, so that two persons' bytes are always in flight behind the one being
+// reduced (many persons: HBM bound).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -29,6 +45,9 @@ constexpr int kLanes = 32;
 constexpr int kThreads = kNK * kLanes;   // 544
 constexpr int kCluster = 4;
 constexpr int kMaxPerThread = 16;        // positions per thread: ceil(2048 / 4 / 32)
+constexpr int kSlots = 3;                // slabs per CTA of the streaming kernel
+constexpr int kStreamSlabBytes = kSlots * (kMaxPerThread * kLanes) * kNK * 4;   // slabs of <= 512 positions: 104448 bytes
+constexpr int kNone = 0x7fffffff;
 
 __device__ float g_exp_one_x0;     // most negative x with exact_expf(x) == 1.0f
 
@@ -57,11 +76,133 @@ __device__ __forceinline__ void cluster_sync_all()
 
 // address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster
 template <typename T>
-__device__ __forceinline__ const T *peer_shared(const T *p, unsigned rank)
+__device__ __forceinline__ T *peer_shared(T *p, unsigned rank)
 {
     unsigned long long out;
     asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(p)), "r"(rank));
-    return reinterpret_cast<const T *>(out);
+    return reinterpret_cast<T *>(out);
+}
+
+// Partials of the four CTAs of a cluster, held by CTA 0 (double buffered for the persistent kernel).
+struct ClusterStats {
+    float m[2][kCluster][kNK];
+    float s[2][kCluster][kNK];
+    int f[2][kCluster][kNK];
+    int near[2][kCluster][kNK];
+};
+
+struct BlockScratch {
+    float m[kNK][kLanes + 1];
+    float s[kNK][kLanes + 1];
+    int f[kNK][kLanes + 1];
+    int rescan[kNK];         // CTA 0: channel needs the exact rescan
+    float gmax[kNK];
+    int found;
+};
+
+__device__ __forceinline__ float exp2f_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// a partial's sum moved onto the common maximum M (s == 0 covers the empty partial, whose m is -inf)
+__device__ __forceinline__ float rescaled(float s, float m, float M) { return s == 0.0f ? 0.0f : fmul(s, __expf(fsub(m, M))); }
+
+// Folds this thread's values (v[i] = logit at position p0 + q + 32 i, -inf where there is none) and merges the CTA's 32
+// partials per channel: warp w reduces channel w and writes its (M, S, F, near) to slot `rank` of buffer `buf` in CTA 0.
+// The kernel is bound by instruction issue, so the per-value work is kept to: max; subtract, compare, mask bit; one fma
+// into the base-2 exponent, ex2, add.
+__device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], int p0, int q, int c, int warp, int lane,
+                                              float x0, BlockScratch &sc, ClusterStats *stats0, int buf, unsigned rank)
+{
+    float m = v[0];
+#pragma unroll
+    for (int i = 1; i < kMaxPerThread; ++i) m = fmaxf(m, v[i]);
+    const float kLog2e = 1.4426950408889634f;
+    const float m2 = m == -__int_as_float(0x7f800000) ? 0.0f : -m * kLog2e;    // empty partial: keep the exponents at -inf
+    float s = 0.0f;
+    unsigned hits = 0u;                                // bit i: exact_expf(v[i] - m) == 1.0f
+#pragma unroll
+    for (int i = 0; i < kMaxPerThread; ++i) {
+        const float d = fsub(v[i], m);
+        hits |= (d >= x0) ? (1u << i) : 0u;
+        s = fadd(s, exp2f_approx(fmaf(v[i], kLog2e, m2)));
+    }
+    const int f = hits ? p0 + q + kLanes * (__ffs(hits) - 1) : kNone;
+    sc.m[c][q] = m; sc.s[c][q] = s; sc.f[c][q] = f;
+    __syncthreads();
+    {   // warp w = channel w: 32 partials -> one
+        const float pm = sc.m[warp][lane];
+        float M = pm;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        float S = rescaled(sc.s[warp][lane], pm, M);
+        int F = (pm == M) ? sc.f[warp][lane] : kNone;
+        const bool near = pm < M && fsub(pm, M) >= x0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {             // butterfly: a fixed summation tree
+            S = fadd(S, __shfl_xor_sync(0xffffffffu, S, o));
+            F = min(F, __shfl_xor_sync(0xffffffffu, F, o));
+        }
+        const unsigned any_near = __ballot_sync(0xffffffffu, near);
+        if (lane == 0) {
+            stats0->m[buf][rank][warp] = M;            // CTA 0's shared memory (local for rank 0, DSMEM otherwise)
+            stats0->s[buf][rank][warp] = S;
+            stats0->f[buf][rank][warp] = F;
+            stats0->near[buf][rank][warp] = any_near != 0u;
+        }
+    }
+}
+
+// CTA 0, after the cluster barrier: merge the four CTAs' partials in fixed order, rescan flagged channels exactly, store.
+__device__ __forceinline__ void cluster_finish(const ClusterStats &st, int buf, BlockScratch &sc, const float *person, int P,
+                                               int n, int crop_h, int crop_w, float x0, float *scores, float *positions,
+                                               int *argmax_out)
+{
+    const int tid = threadIdx.x;
+    float S = 0.0f;
+    int F = kNone;
+    int near = 0;
+    if (tid < kNK) {
+        float M = st.m[buf][0][tid];
+        for (int r = 1; r < kCluster; ++r) M = fmaxf(M, st.m[buf][r][tid]);
+        for (int r = 0; r < kCluster; ++r) {           // fixed order: CTA 0, 1, 2, 3
+            const float m = st.m[buf][r][tid];
+            S = fadd(S, rescaled(st.s[buf][r][tid], m, M));
+            if (m == M) F = min(F, st.f[buf][r][tid]);
+            // a near tie inside a CTA matters only if that CTA's maximum is itself within reach of M
+            near |= (st.near[buf][r][tid] != 0 || m < M) && fsub(m, M) >= x0;
+        }
+        sc.rescan[tid] = near;
+        sc.gmax[tid] = M;
+    }
+    // exact rescan (block-uniform decision; practically never taken): first position with l - M >= x0
+    if (__syncthreads_or(near)) {
+        for (int ch = 0; ch < kNK; ++ch) {
+            if (!sc.rescan[ch]) continue;              // uniform
+            __syncthreads();
+            if (tid == 0) sc.found = kNone;
+            __syncthreads();
+            const float M = sc.gmax[ch];
+            int best = kNone;
+            for (int p = tid; p < P; p += kThreads)
+                if (fsub(__ldcg(person + (size_t)p * kNK + ch), M) >= x0) { best = p; break; }
+            if (best != kNone) atomicMin(&sc.found, best);
+            __syncthreads();
+            if (tid == ch) F = sc.found;
+        }
+    }
+    if (tid < kNK) {
+        if (F == kNone) F = 0;                         // only with NaN logits
+        const float rcp = fdiv(1.0f, S);
+        const size_t o = (size_t)n * kNK + tid;
+        scores[o] = fmul(1.0f, rcp);
+        positions[o * 2 + 0] = fdiv((float)(F / crop_w), (float)crop_h);
+        positions[o * 2 + 1] = fdiv((float)(F % crop_w), (float)crop_w);
+        if (argmax_out) argmax_out[o] = F;
+    }
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
@@ -69,12 +210,8 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
                        const int crop_w, float *__restrict__ scores, float *__restrict__ positions,
                        int *__restrict__ argmax_out)
 {
-    __shared__ float s_f[kNK][kLanes + 1];
-    __shared__ int s_i[kNK][kLanes + 1];
-    __shared__ float s_max[kNK];          // this CTA's per-channel maximum (read by the peers)
-    __shared__ float s_sum[kNK];          // this CTA's per-channel sum of exp(l - global max)
-    __shared__ int s_first[kNK];          // this CTA's first position with exp(l - global max) == 1
-    __shared__ float s_gmax[kNK];
+    __shared__ BlockScratch sc;
+    __shared__ ClusterStats stats;        // used in CTA 0 only
     const int n = blockIdx.x / kCluster;
     const unsigned rank = cluster_rank();
     pdl_trigger();
@@ -85,72 +222,105 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
     const int per = (P + kCluster - 1) / kCluster;
     const int p0 = (int)rank * per, p1 = min(P, p0 + per);
     const int tid = threadIdx.x, c = tid % kNK, q = tid / kNK;
-    const float *row = logits + (size_t)n * P * kNK + (size_t)p0 * kNK;
+    const float *person = logits + (size_t)n * P * kNK;
+    const float *row = person + (size_t)p0 * kNK;
     float v[kMaxPerThread];
-    float lmax = -__int_as_float(0x7f800000);
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-        const int p = p0 + q + kLanes * i;
-        v[i] = (p < p1) ? __ldcs(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
-        lmax = fmaxf(lmax, v[i]);
+    for (int i = 0; i < kMaxPerThread; ++i)
+        v[i] = (p0 + q + kLanes * i < p1) ? __ldcs(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
+    slab_partials(v, p0, q, c, tid >> 5, tid & 31, g_exp_one_x0, sc, peer_shared(&stats, 0), 0, rank);
+    cluster_sync_all();                   // all partials have landed in CTA 0; the peers are done
+    if (rank == 0) cluster_finish(stats, 0, sc, person, P, n, crop_h, crop_w, g_exp_one_x0, scores, positions, argmax_out);
+}
+
+// ---- streaming variant ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void slab_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned addr = smem_addr(bar);
+    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
     }
-    const int warp = tid >> 5, lane = tid & 31;       // 17 warps: warp w folds the 32 partials of channel w
-    s_f[c][q] = lmax;
+    __trap();      // a protocol bug is reported as a CUDA error instead of hanging the GPU
+}
+
+// one thread: request `bytes` (multiple of 16) of global memory into shared memory, completion on `bar`
+__device__ __forceinline__ void slab_fetch(float *dst, const float *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of dst are done (bar.sync)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__restrict__ n_dev, const int n_host,
+                              const int crop_h, const int crop_w, float *__restrict__ scores,
+                              float *__restrict__ positions, int *__restrict__ argmax_out)
+{
+    extern __shared__ __align__(128) float s_slab[];      // kSlots x slab_floats
+    __shared__ unsigned long long s_bar[kSlots];
+    __shared__ BlockScratch sc;
+    __shared__ ClusterStats stats;        // used in CTA 0 only
+    const unsigned rank = cluster_rank();
+    const int n_clusters = gridDim.x / kCluster;
+    const int tid = threadIdx.x, c = tid % kNK, q = tid / kNK;
+    const int P = crop_h * crop_w;
+    const int per = (P + kCluster - 1) / kCluster;        // per * 17 * 4 bytes is a multiple of 16 (checked by the host)
+    const int p0 = (int)rank * per, p1 = min(P, p0 + per);
+    const int slab_floats = per * kNK;
+    const unsigned bytes = (unsigned)max(p1 - p0, 0) * kNK * 4u;
+    pdl_trigger();
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();                           // the PRN has completed
     __syncthreads();
-    {
-        float m = s_f[warp][lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) s_max[warp] = m;
-    }
-    cluster_sync_all();                   // every CTA's s_max is visible cluster-wide
-    if (tid < kNK) {
-        float m = s_max[tid];
-        for (unsigned r = 0; r < kCluster; ++r)
-            if (r != rank) m = fmaxf(m, *peer_shared(&s_max[tid], r));
-        s_gmax[tid] = m;
-    }
-    __syncthreads();
-    lmax = s_gmax[c];
+    const int N = n_dev ? *n_dev : n_host;
     const float x0 = g_exp_one_x0;
-    float sum = 0.0f;
-    int first = 0x7fffffff;
+    ClusterStats *stats0 = peer_shared(&stats, 0);
+    int n = blockIdx.x / kCluster;
+    if (tid == 0 && bytes)
+        for (int j = 0; j < kSlots - 1; ++j) {
+            const long long nj = (long long)n + (long long)j * n_clusters;
+            if (nj < N) slab_fetch(s_slab + j * slab_floats, logits + (size_t)nj * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[j]);
+        }
+    for (int it = 0; n < N; ++it, n += n_clusters) {       // uniform over the cluster
+        const int slot = it % kSlots;
+        const float *src = s_slab + slot * slab_floats;
+        // slot (it - 1) % kSlots was last read in iteration it - 1, which every thread left through a cluster barrier
+        const long long n_ahead = (long long)n + (long long)(kSlots - 1) * n_clusters;
+        if (tid == 0 && n_ahead < N && bytes) {
+            const int sa = (it + kSlots - 1) % kSlots;
+            slab_fetch(s_slab + sa * slab_floats, logits + (size_t)n_ahead * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[sa]);
+        }
+        if (bytes) slab_wait(&s_bar[slot], (unsigned)(it / kSlots) & 1u);
+        float v[kMaxPerThread];
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-        const int p = p0 + q + kLanes * i;
-        if (p < p1) {
-            const float d = fsub(v[i], lmax);
-            sum = fadd(sum, __expf(d));
-            if (d >= x0 && p < first) first = p;       // <=> exact_expf(d) == 1.0f
-        }
+        for (int i = 0; i < kMaxPerThread; ++i)
+            v[i] = (p0 + q + kLanes * i < p1) ? src[tid + kThreads * i] : -__int_as_float(0x7f800000);
+        // partials of iteration it go to buffer it & 1 of CTA 0: CTA 0 read it last in iteration it - 2, i.e. before it
+        // arrived at the barrier of iteration it - 1, which this CTA has already passed
+        slab_partials(v, p0, q, c, tid >> 5, tid & 31, x0, sc, stats0, it & 1, rank);
+        cluster_sync_all();               // all partials of this person have landed in CTA 0
+        if (rank == 0)
+            cluster_finish(stats, it & 1, sc, logits + (size_t)n * P * kNK, P, n, crop_h, crop_w, x0, scores, positions,
+                           argmax_out);
     }
-    s_f[c][q] = sum; s_i[c][q] = first;
-    __syncthreads();
-    {
-        float S = s_f[warp][lane]; int best = s_i[warp][lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {          // butterfly: a fixed summation tree
-            S = fadd(S, __shfl_xor_sync(0xffffffffu, S, o));
-            best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        }
-        if (lane == 0) { s_sum[warp] = S; s_first[warp] = best; }
-    }
-    cluster_sync_all();                   // every CTA's s_sum / s_first is visible cluster-wide
-    if (rank == 0 && tid < kNK) {
-        float S = s_sum[tid]; int best = s_first[tid];
-        for (unsigned r = 1; r < kCluster; ++r) {          // fixed order: CTA 0, 1, 2, 3
-            S = fadd(S, *peer_shared(&s_sum[tid], r));
-            best = min(best, *peer_shared(&s_first[tid], r));
-        }
-        if (best == 0x7fffffff) best = 0;    // only with NaN logits
-        const float rcp = fdiv(1.0f, S);
-        const size_t o = (size_t)n * kNK + tid;
-        scores[o] = fmul(1.0f, rcp);
-        positions[o * 2 + 0] = fdiv((float)(best / crop_w), (float)crop_h);
-        positions[o * 2 + 1] = fdiv((float)(best % crop_w), (float)crop_w);
-        if (argmax_out) argmax_out[o] = best;
-    }
-    cluster_sync_all();                   // peers stay alive until CTA 0 has read their shared memory
+    // (no barrier on the way out: after the last in-loop barrier nobody touches another CTA's shared memory)
 }
 
 }  // namespace
@@ -158,7 +328,10 @@ keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__
 int kpdecode_prepare(cudaStream_t s)
 {
     exp_one_threshold_kernel<<<1, 1, 0, s>>>();
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    // the streaming kernel's slab ring: sized for the default 56 x 36 crop and anything smaller
+    return cudaFuncSetAttribute(keypoint_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kStreamSlabBytes) == cudaSuccess ? 0 : -1;
 }
 
 int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
@@ -166,6 +339,26 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
 {
     if (n_max <= 0) return 0;
     if (crop_h * crop_w > kMaxPerThread * kLanes * kCluster) return -(int)cudaErrorInvalidValue;
+    const int P = crop_h * crop_w, per = (P + kCluster - 1) / kCluster;
+    static const char *force = getenv("MPN_TUNE_DECODE");      // development: "0" register kernel, "1" streaming kernel
+    const bool stream_ok = (per % 4 == 0) && (P % 4 == 0) && kSlots * per * kNK * 4 <= kStreamSlabBytes;
+    const bool want_stream = force ? force[0] == '1' : true;   // measured faster at every person count (94.5 vs 96.1 us per c2 step)
+    if (stream_ok && want_stream) {
+        static int resident = 0;          // clusters that fit the device at once
+        if (resident == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kStreamSlabBytes;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel, &cfg) != cudaSuccess || n < 1) n = 64;
+            cudaGetLastError();
+            resident = n;
+        }
+        const int clusters = n_max < resident ? n_max : resident;
+        prof_mark(s, "keypoint_decode");
+        launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)kStreamSlabBytes, s, true,
+                 logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
+        return 1;
+    }
     prof_mark(s, "keypoint_decode");
     launch_k(keypoint_decode_kernel, dim3(n_max * kCluster), dim3(kThreads), 0, s, true, logits, n_dev, n_host, crop_h, crop_w,
              scores, positions, argmax);

@@ -349,6 +349,47 @@ def test_keypoint_decode_argmax_bit_exact(det6, prn_weights):
     assert arg[1, 2] == 40 * 36 + 7 and arg[2, 9] == 10 * 36 + 3
 
 
+def test_keypoint_decode_near_ties_take_the_exact_rescan(det6):
+    """Two DIFFERENT logits so close that exp(l - max) is 1.0f for both (only possible for small |max|): the reference
+    rule (first index of the maximal fp32 probability) then picks the earlier position even when it holds the smaller
+    logit.  The one-pass decode flags such channels and rescans them exactly."""
+    rng = np.random.default_rng(5)
+    for n in (6, 170):                                  # register kernel, streaming kernel
+        logits = rng.normal(-3.0, 0.5, (n, 56, 36, 17)).astype(np.float32)
+        cases = [(0, 0, 0.3, 1), (1, 3, 0.3, 2), (2, 5, 0.1, 1), (3, 7, 0.01, 3), (4, 16, 0.45, 1), (5, 9, 0.02, 40)]
+        for person, ch, mx, ulps in cases:
+            below = np.float32(mx)
+            for _ in range(ulps):
+                below = np.nextafter(below, np.float32(0))
+            logits[person, 50, 30, ch] = mx             # the maximum, late (last quarter of the positions)
+            logits[person, 2, 5, ch] = below            # slightly smaller, early (first quarter, another CTA)
+            logits[person, 30, 1, ch] = below           # and in between
+        s, pos, arg, gap = oracle.keypoint_decode(logits)
+        gs, gpos, garg = det6.keypoint_decode(_cuda(logits))
+        assert_bit_equal(garg.cpu().numpy(), arg, f"argmax n={n}")
+        assert_bit_equal(gpos.cpu().numpy(), pos, f"positions n={n}")
+        np.testing.assert_allclose(gs.cpu().numpy(), s, rtol=RTOL_FP32)
+        picked = [int(arg[p, c]) for p, c, _, _ in cases]
+        assert 2 * 36 + 5 in picked and 50 * 36 + 30 in picked      # both outcomes occur
+
+
+def test_keypoint_decode_streaming_kernel_many_persons(det6):
+    """>= 160 persons per call: the persistent, bulk-copy fed decode kernel (clusters walk the persons, three slabs in
+    flight).  More persons than resident clusters, a count that is not a multiple of anything, planted ties."""
+    rng = np.random.default_rng(77)
+    n = 523
+    logits = rng.normal(0.0, 1.0, (n, 56, 36, 17)).astype(np.float32)
+    logits[5, :, :, 3] = -0.5                          # all-equal channel
+    logits[200, 55, 35, 16] = 40.0                     # last position, last channel
+    logits[522, 0, 0, 0] = logits[522, 17, 9, 0] = 9.0  # exact tie in the last person -> first index
+    s, pos, arg, gap = oracle.keypoint_decode(logits)
+    gs, gpos, garg = det6.keypoint_decode(_cuda(logits))
+    assert_bit_equal(garg.cpu().numpy(), arg, "argmax")
+    assert_bit_equal(gpos.cpu().numpy(), pos, "positions")
+    np.testing.assert_allclose(gs.cpu().numpy(), s, rtol=RTOL_FP32)
+    assert arg[5, 3] == 0 and arg[200, 16] == 2015 and arg[522, 0] == 0
+
+
 def test_get_keypoints_matches_reference_golden_vectors(det6):
     """tests/golden/get_keypoints.npz holds outputs of the reference's own inference/utils.py::get_keypoints."""
     import os
