@@ -29,8 +29,8 @@
 // cluster barrier, then CTA 0 merges and stores.  Two kernels share this arithmetic: keypoint_decode_kernel, one cluster
 // per person with the logits loaded straight into registers (lowest latency, few persons), and
 // keypoint_decode_stream_kernel, PERSISTENT clusters that walk the persons with every CTA's slab arriving by one bulk
-// copy (TMA) into a three-slot shared-memory ring, so that two persons' bytes are always in flight behind the one being
-// reduced (many persons: HBM bound).
+// copy (TMA) into a two-slot shared-memory ring, three CTAs per SM, so that the next person's bytes are in flight while
+// the current one is reduced (many persons: HBM bound).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,8 +45,8 @@ constexpr int kLanes = 32;
 constexpr int kThreads = kNK * kLanes;   // 544
 constexpr int kCluster = 4;
 constexpr int kMaxPerThread = 16;        // positions per thread: ceil(2048 / 4 / 32)
-constexpr int kSlots = 3;                // slabs per CTA of the streaming kernel
-constexpr int kStreamSlabBytes = kSlots * (kMaxPerThread * kLanes) * kNK * 4;   // slabs of <= 512 positions: 104448 bytes
+constexpr int kSlots = 2;                // slabs per CTA of the streaming kernel (three CTAs per SM: six slabs per SM)
+constexpr int kStreamSlabBytes = kSlots * (kMaxPerThread * kLanes) * kNK * 4;   // upper bound: slabs of 512 positions
 constexpr int kNone = 0x7fffffff;
 
 __device__ float g_exp_one_x0;     // most negative x with exact_expf(x) == 1.0f
@@ -84,20 +84,21 @@ __device__ __forceinline__ T *peer_shared(T *p, unsigned rank)
 }
 
 // Partials of the four CTAs of a cluster, held by CTA 0 (double buffered for the persistent kernel).
+// Shared memory is what limits the streaming kernel to three CTAs per SM (2 x 34272 bytes of slabs each), so the
+// scratch is packed: 76800 bytes per CTA are available, the slabs take 68544.
 struct ClusterStats {
     float m[2][kCluster][kNK];
     float s[2][kCluster][kNK];
-    int f[2][kCluster][kNK];
-    int near[2][kCluster][kNK];
+    int f[2][kCluster][kNK];              // first qualifying position, kNone if none; NEGATIVE (~f) when the CTA saw a near tie
 };
 
 struct BlockScratch {
-    float m[kNK][kLanes + 1];
-    float s[kNK][kLanes + 1];
-    int f[kNK][kLanes + 1];
-    int rescan[kNK];         // CTA 0: channel needs the exact rescan
+    float m[kThreads];                    // indexed by thread (q * 17 + c): conflict-free both ways (17 is odd)
+    float s[kThreads];
+    unsigned short hits[kThreads];        // bit i: value i of the thread reaches the thread's maximum (exp == 1)
     float gmax[kNK];
     int found;
+    unsigned char rescan[kNK + 3];        // CTA 0: channel needs the exact rescan
 };
 
 __device__ __forceinline__ float exp2f_approx(float x)
@@ -130,16 +131,18 @@ __device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], i
         hits |= (d >= x0) ? (1u << i) : 0u;
         s = fadd(s, exp2f_approx(fmaf(v[i], kLog2e, m2)));
     }
-    const int f = hits ? p0 + q + kLanes * (__ffs(hits) - 1) : kNone;
-    sc.m[c][q] = m; sc.s[c][q] = s; sc.f[c][q] = f;
+    const int me = q * kNK + c;                        // == threadIdx.x
+    sc.m[me] = m; sc.s[me] = s; sc.hits[me] = (unsigned short)hits;
     __syncthreads();
-    {   // warp w = channel w: 32 partials -> one
-        const float pm = sc.m[warp][lane];
+    {   // warp w = channel w: the 32 partials (q = lane) -> one
+        const int src = lane * kNK + warp;
+        const float pm = sc.m[src];
         float M = pm;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
-        float S = rescaled(sc.s[warp][lane], pm, M);
-        int F = (pm == M) ? sc.f[warp][lane] : kNone;
+        float S = rescaled(sc.s[src], pm, M);
+        const unsigned h = sc.hits[src];
+        int F = (pm == M && h) ? p0 + lane + kLanes * (__ffs(h) - 1) : kNone;
         const bool near = pm < M && fsub(pm, M) >= x0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {             // butterfly: a fixed summation tree
@@ -150,8 +153,7 @@ __device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], i
         if (lane == 0) {
             stats0->m[buf][rank][warp] = M;            // CTA 0's shared memory (local for rank 0, DSMEM otherwise)
             stats0->s[buf][rank][warp] = S;
-            stats0->f[buf][rank][warp] = F;
-            stats0->near[buf][rank][warp] = any_near != 0u;
+            stats0->f[buf][rank][warp] = any_near ? ~F : F;
         }
     }
 }
@@ -170,12 +172,13 @@ __device__ __forceinline__ void cluster_finish(const ClusterStats &st, int buf, 
         for (int r = 1; r < kCluster; ++r) M = fmaxf(M, st.m[buf][r][tid]);
         for (int r = 0; r < kCluster; ++r) {           // fixed order: CTA 0, 1, 2, 3
             const float m = st.m[buf][r][tid];
+            const int fr = st.f[buf][r][tid];
             S = fadd(S, rescaled(st.s[buf][r][tid], m, M));
-            if (m == M) F = min(F, st.f[buf][r][tid]);
+            if (m == M) F = min(F, fr < 0 ? ~fr : fr);
             // a near tie inside a CTA matters only if that CTA's maximum is itself within reach of M
-            near |= (st.near[buf][r][tid] != 0 || m < M) && fsub(m, M) >= x0;
+            near |= (fr < 0 || m < M) && fsub(m, M) >= x0;
         }
-        sc.rescan[tid] = near;
+        sc.rescan[tid] = (unsigned char)near;
         sc.gmax[tid] = M;
     }
     // exact rescan (block-uniform decision; practically never taken): first position with l - M >= x0
@@ -265,7 +268,7 @@ __device__ __forceinline__ void slab_fetch(float *dst, const float *src, unsigne
                  : "memory");
 }
 
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+__global__ void __cluster_dims__(kCluster, 1, 1) __maxnreg__(40)
 keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__restrict__ n_dev, const int n_host,
                               const int crop_h, const int crop_w, float *__restrict__ scores,
                               float *__restrict__ positions, int *__restrict__ argmax_out)
@@ -347,7 +350,7 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
         static int resident = 0;          // clusters that fit the device at once
         if (resident == 0) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kStreamSlabBytes;
+            cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSlots * per * kNK * 4;
             int n = 0;
             if (cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel, &cfg) != cudaSuccess || n < 1) n = 64;
             cudaGetLastError();
@@ -355,7 +358,7 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
         }
         const int clusters = n_max < resident ? n_max : resident;
         prof_mark(s, "keypoint_decode");
-        launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)kStreamSlabBytes, s, true,
+        launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)(kSlots * per * kNK * 4), s, true,
                  logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
         return 1;
     }
