@@ -188,7 +188,9 @@ MPN_API int mpn_heatmap_head(mpn_handle *h, const float *features, const float *
 MPN_API int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
              int32_t hm_width, const float *boxes, const int32_t *box_ind, int32_t n, float *crops, void *stream);
 
-/* detector/prn.py:5-25: crops [N, D] f32 -> logits [N, D] f32 */
+/* detector/prn.py:5-25: crops [N, D] f32 -> logits [N, D] f32.  logits == crops (bf16 mode only) computes in place:
+ * x += relu(fc2(relu(fc1(x)))), which is how mpn_run uses it (the residual addition then happens in L2 by a TMA
+ * reduce-add and the layer never loads x).                                                                   */
 MPN_API int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, float *logits, void *stream);
 
 /* create_pb.py:115-142: logits [N, crop_h*crop_w, K] -> scores [N,K], positions [N,K,2], argmax [N,K] i32 (optional) */

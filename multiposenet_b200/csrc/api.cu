@@ -550,6 +550,9 @@ int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, floa
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) { h->last_launches = 0; return MPN_OK; }
+    if (crops == logits && (prn_mode != MPN_PRN_BF16 || !(h->big || (h->fused && n <= kPrnFusedMaxRows))))
+        return fail(h, MPN_ERR_UNSUPPORTED, "in-place PRN (logits == crops) needs bf16 mode and a covered shape");
+    ProfScope prof_scope(h, s);                        // per-kernel times of this call when profiling is on
     bool first = true;
     if (prn_mode == MPN_PRN_BF16) {
         if (!h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
@@ -656,11 +659,14 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
                       false, "crop");
     if (rc) return rc;
     // 4. PRN                                                 (detector/prn.py:5-25)
-    if (!(skip & 16u)) rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, h->logits, s, false);
+    // bf16 mode: in place -- the logits overwrite the fp32 crops (the large-batch fc2 then adds the residual in L2 with a
+    // TMA reduce-add instead of loading it; the single-kernel PRN loads and stores every element in the same thread)
+    float *prn_out = (bf16 && (h->big || (h->fused && n_max <= kPrnFusedMaxRows))) ? h->crops_f32 : h->logits;
+    if (!(skip & 16u)) rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, prn_out, s, false);
     if (rc) return rc;
     // 5. softmax / argmax                                    (create_pb.py:115-142)
     if (skip & 32u) return MPN_OK;
-    return launched(h, launch_keypoint_decode(h->logits, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
+    return launched(h, launch_keypoint_decode(prn_out, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
                                               out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
                     "keypoint decode");
 }

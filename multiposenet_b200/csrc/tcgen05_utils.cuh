@@ -172,6 +172,33 @@ inline bool encode_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 row-major [rows, cols] matrix, box = box_rows x 16 columns (64-byte rows), 64-byte swizzle: the layout of the
+// per-warp transpose buffers (stage_write) -- used for TMA reduce-add stores of accumulator chunks
+inline bool encode_2d_f32_chunk(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 4};
+    const cuuint32_t box[2] = {16, box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, elem,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// one thread: global[box at (c0, c1)] += shared box (fp32 add performed in L2), as one bulk-async group
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *tmap, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's earlier bulk-async groups have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace mpn

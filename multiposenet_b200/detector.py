@@ -409,10 +409,11 @@ class Detector:
                                            _ptr(box_ind), N, _ptr(out), self._stream()))
         return out
 
-    def prn(self, crops, prn_mode=None):
-        """detector/prn.py:5-25 -> logits, same shape as crops."""
+    def prn(self, crops, prn_mode=None, inplace=False):
+        """detector/prn.py:5-25 -> logits, same shape as crops.  inplace=True (bf16 mode) overwrites `crops` with the
+        logits, as the full path does internally."""
         N = int(crops.shape[0])
-        out = torch.empty_like(crops)
+        out = crops if inplace else torch.empty_like(crops)
         mode = _mode_id(self.config.prn_mode if prn_mode is None else prn_mode)
         self._check(self._lib.mpn_prn(self._handle, _ptr(crops), N, mode, _ptr(out), self._stream()))
         return out
