@@ -76,6 +76,7 @@ struct FusedArgs {
 
 struct FusedMaps {
     CUtensorMap x, w1, y1, w2;
+    CUtensorMap out;           // fp32 chunk boxes over the buffer of the in-place call (re-encoded when it changes)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
@@ -135,10 +136,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
+// kInPlace: logits == x (how mpn_run calls it).  The fc2 epilogue then never loads the residual: bias and ReLU are applied
+// in registers, the chunk goes to the warp's transpose buffer (a 64-byte-swizzled TMA box) and a TMA reduce-add performs
+// x += y2 in L2 -- the same single fp32 rounding, no residual registers, 4 B / element less L2 -> SM traffic.
+template <bool kInPlace>
 __global__ void __launch_bounds__(kThreads, 1)
 prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,
-                 const FusedArgs args)
+                 const __grid_constant__ CUtensorMap tmap_out, const FusedArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
@@ -439,7 +444,38 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 reinterpret_cast<float4 *>(s_b2)[tid_e] =
                     n < args.D ? __ldg(reinterpret_cast<const float4 *>(args.b2 + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            for (int m = 0; m < nm; ++m) {
+            if (kInPlace) {
+                epi_bar_sync();                                             // s_b2 visible
+                mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
+                tc_fence_after();
+                if (tid_e == 0) stamp(args, 9);                             // fc2 accumulators complete
+                for (int m = 0; m < nm; ++m) {
+                    const int row0 = m * 128 + q * 32;
+                    if (row0 >= N) break;                                   // warp-uniform
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (cg * 64 + ch * 16 >= kFc2N) break;              // warp-uniform (last column group: 3 chunks)
+                        uint32_t r[16];
+                        tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = *reinterpret_cast<const float4 *>(s_b2 + cg * 64 + ch * 16 + 4 * j);   // broadcast
+                            r[4 * j + 0] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 0]), b.x), 0.0f));
+                            r[4 * j + 1] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 1]), b.y), 0.0f));
+                            r[4 * j + 2] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 2]), b.z), 0.0f));
+                            r[4 * j + 3] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 3]), b.w), 0.0f));
+                        }
+                        if (lane == 0) tma_store_wait_read();               // the previous chunk has left the buffer
+                        __syncwarp();
+                        stage_write(stg, lane, r);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        // rows N .. of the last 32-row box receive meaningless sums; nothing ever reads them
+                        if (lane == 0) tma_reduce_add_2d(&tmap_out, stg, n0 + cg * 64 + ch * 16, row0);
+                    }
+                }
+            }
+            for (int m = 0; m < nm && !kInPlace; ++m) {
                 const int row0 = m * 128 + q * 32;
                 const bool rows_live = row0 < N;                            // warp-uniform
                 const int col_base = cg * 64 + sub_col;                     // column of this lane inside the tile, chunk 0
@@ -494,6 +530,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (tid_e == 0) stamp(args, 15);                                // warp 2 finished the fc2 epilogue
             epi_bar_sync();                                                 // s_b2 may be overwritten by the next tile
         }
+        if (kInPlace && lane == 0) tma_store_wait_all();                    // this thread's reduce-adds have completed
         if (tid_e == 0) stamp(args, 10);                                    // logits stored
     }
     tc_fence_before();
@@ -510,6 +547,7 @@ struct FusedState {
     unsigned long long *bar;   // grid barrier arrival counter
     unsigned long long *trace;
     int grid, splits, rows_cap;
+    const float *out_ptr;      // buffer maps.out describes (handle-owned buffers only)
 };
 
 int prn_fused_prepare(mpn_handle *h)
@@ -520,8 +558,9 @@ int prn_fused_prepare(mpn_handle *h)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop || sms < kHq) return MPN_OK;
-    if (cudaFuncSetAttribute(prn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel, kThreads, kSmemBytes) != cudaSuccess ||
+    if (cudaFuncSetAttribute(prn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(prn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel<true>, kThreads, kSmemBytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         snprintf(h->err, sizeof(h->err), "prn_fused_kernel cannot be made resident (smem %d)", kSmemBytes);
@@ -616,7 +655,16 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, prn_fused_kernel, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2, a);
+    const bool in_place = x_f32 == logits;
+    if (in_place && st->out_ptr != logits) {
+        const uint64_t rows = n_dev ? (uint64_t)h->prn_ws.n_max : (uint64_t)n_host;    // mpn_prn: the caller's buffer has n_host rows
+        if (!encode_2d_f32_chunk(&st->maps.out, logits, rows, (uint64_t)h->D, 32)) return -(int)cudaErrorInvalidValue;
+        st->out_ptr = n_dev ? logits : nullptr;        // a caller's buffer may change size between calls: never cached
+    }
+    cudaError_t e = in_place ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true>, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2,
+                                                  st->maps.out, a)
+                             : cudaLaunchKernelEx(&cfg, prn_fused_kernel<false>, st->maps.x, st->maps.w1, st->maps.y1,
+                                                  st->maps.w2, st->maps.out, a);
     if (e != cudaSuccess) return -(int)e;
     return 1;
 }

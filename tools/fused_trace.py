@@ -11,7 +11,7 @@ det = Detector(w, DetectorConfig(max_batch=8, max_boxes=32, prn_mode="bf16", prn
 x = torch.from_numpy(synthetic.make_crops(n)).cuda()
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 for _ in range(3):
-    det.prn(x, "bf16")
+    det.prn(x, "bf16", inplace=True)
 det.fused_trace(True)
 names = {7: "pdl wait passed", 0: "prologue", 1: "fc1 loads issued", 2: "fc1 mma issued", 3: "fc1 acc complete", 4: "partials stored",
          11: "w2 fc2 chunk0 in regs", 12: "w2 fc2 next loads issued", 13: "w2 fc2 chunk0 transposed", 14: "w2 fc2 chunk 0 stored",
@@ -22,7 +22,7 @@ for rep in range(3):
     for i in range(300):
         if i == 100:
             e0.record()
-        det.prn(x, "bf16")
+        det.prn(x, "bf16", inplace=True)
     e1.record(); torch.cuda.synchronize()
     t = det.fused_trace(True).astype(np.int64)
     t0 = t[:, 0].min()
