@@ -138,7 +138,8 @@ def algorithmic_bytes(kernel, wl, B, n_persons, n_cand, mode):
         "sort_nms": 8 * n_cand + 16 * n_cand + B * wl.max_detections * 20,
         "heatmap": 72 * pix * B + 72 * pix * B,
         "crop": n_persons * D * (4 + (2 if mode == "bf16" else 0)),
-        "prn_fused": 2 * D * HIDDEN * 2 + n_persons * D * (2 + 4 + 4),   # both weight matrices once, x, residual, logits
+        # both weight matrices once, x in bf16, residual read and logits written (in place); launched but idle above 256 persons
+        "prn_fused": None if n_persons > 256 else 2 * D * HIDDEN * 2 + n_persons * D * (2 + 4 + 4),
         "prn_bf16_fc1": D * HIDDEN * 2 + n_persons * D * 2,
         "prn_bf16_fc2": D * HIDDEN * 2 + n_persons * (HIDDEN * 2 + D * 4 + D * 4),
         "prn_fp32_fc1": D * HIDDEN * 4 + n_persons * D * 4,
@@ -386,14 +387,17 @@ def main():
             ab = algorithmic_bytes(name, wl, B, persons, n_cand, args.prn_mode)
             kernels[name] = {"ms": round(ms, 5), "share": round(ms / step_ms, 4),
                              "alg_bytes": ab, "gbs": None if not ab else round(ab / ms / 1e6, 1)}
+            if name in ("prn_big_fc1", "prn_big_fc2", "prn_bf16_fc1", "prn_bf16_fc2"):      # tensor-bound layers: 2 N D H flop
+                kernels[name]["tflops"] = round(2.0 * persons * D * HIDDEN / ms / 1e9, 1)
         top = max([n for n in order if kernels[n]["alg_bytes"]], key=lambda n: statistics.mean(acc[n]))
         ab = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
         ach = ab / statistics.mean(acc[top]) / 1e6
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
-        except Exception:
-            pass
+        if args.workload == "c2":          # the committed ncu capture was taken at this workload's sizes
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+            except Exception:
+                pass
         launch_ms = statistics.mean(acc[top])
         timing = "CUDA events between direct launches (profiling pass)"
         if top == "prn_fused":
