@@ -250,7 +250,7 @@ __device__ __forceinline__ float normalise_tap(float v, float m, float M, float 
 __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
                                                         const int npix, float *__restrict__ nh)
 {
-    __shared__ float s_m[kPadCh], s_d[kPadCh], s_mask[kPadCh];
+    __shared__ float s_m[kPadCh], s_d[kPadCh], s_mask[kPadCh], s_rcp[kPadCh];
     const int img = blockIdx.y;
     pdl_trigger();
     pdl_wait();                                        // the heatmap kernel (min / max fold included) has completed
@@ -258,9 +258,15 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict_
         const bool real = threadIdx.x < kNK;
         const float m = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2) : 0.0f;
         const float M = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2 + 1) : 1.0f;
+        const float d = fsub(M, m);
         s_m[threadIdx.x] = m;
-        s_d[threadIdx.x] = fsub(M, m);
+        s_d[threadIdx.x] = d;
         s_mask[threadIdx.x] = (real && M > 0.2f) ? 1.0f : 0.0f;
+        // Division by the channel's constant range, one IEEE division per heatmap value (the kernel is issue bound on it):
+        // with y = RN(1 / d), q = RN(a y), the correction q' = fma(fma(-q, d, a), y, q) IS the correctly rounded a / d
+        // for 0 <= a <= d, d >= 2^-60 and a == 0 or a >= 1e-30 (tools/div_check.cu: 10^10 pairs incl. the all-ones /
+        // all-zeros mantissas, 0 mismatches; subnormal a does differ).  0 marks a channel that takes the true division.
+        s_rcp[threadIdx.x] = (d >= 8.67361738e-19f) ? __frcp_rn(d) : 0.0f;      // 2^-60; false for NaN and for M == m
     }
     __syncthreads();
     const float *src = kh + (size_t)img * npix * kNK;
@@ -273,7 +279,15 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict_
         for (int k = 0; k < 4; ++k) {
             const int c = 4 * g + k;
             const float v = c < kNK ? __ldcg(src + (size_t)p * kNK + c) : 0.0f;
-            o[k] = c < kNK ? fmul(fdiv(fsub(v, s_m[c]), s_d[c]), s_mask[c]) : 0.0f;
+            const float a = fsub(v, s_m[c]), y = s_rcp[c];
+            float q;
+            if (y == 0.0f || (a != 0.0f && a < 1e-30f)) {
+                q = fdiv(a, s_d[c]);
+            } else {
+                const float q0 = fmul(a, y);
+                q = __fmaf_rn(__fmaf_rn(-q0, s_d[c], a), y, q0);
+            }
+            o[k] = c < kNK ? fmul(q, s_mask[c]) : 0.0f;
         }
         dst[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
