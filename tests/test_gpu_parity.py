@@ -311,6 +311,53 @@ def test_prn_tiled_fallback_kernels(prn_weights, monkeypatch):
         det.close()
 
 
+@pytest.mark.parametrize("n", [70, 300, 700])
+def test_prn_in_place_equals_out_of_place_bit_for_bit(det6, prn_weights, n):
+    """logits == crops: the residual addition is a TMA reduce-add performed in L2 (single-kernel PRN for <= 256 persons,
+    large-batch fc2 on CTA pairs above) instead of load / add / store -- the same single fp32 rounding, so the same
+    bits; fp32 mode refuses to run in place."""
+    x = synthetic.make_crops(n, seed=200 + n)
+    want = det6.prn(_cuda(x), "bf16").cpu().numpy()
+    buf = _cuda(x)
+    got = det6.prn(buf, "bf16", inplace=True)
+    assert got.data_ptr() == buf.data_ptr()
+    assert_bit_equal(got.cpu().numpy(), want, f"in place n={n}")
+    with pytest.raises(Exception):
+        det6.prn(_cuda(x), "fp32", inplace=True)
+
+
+def test_single_cta_fc2_and_no_pdl_paths_give_the_same_bits(prn_weights, monkeypatch):
+    """MPN_FC2_PAIRS=0 (large-batch fc2 on single CTAs) and MPN_NO_PDL=1 (no programmatic dependent launch) are kept as
+    switches: both must reproduce the default path bit for bit."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    wl = synthetic.WORKLOADS["c3"]
+    inp = synthetic.make_inputs(wl, batch=3)
+    cfg = dict(max_batch=3, max_height=640, max_width=640, max_boxes=128, score_threshold=0.3, iou_threshold=0.5,
+               scale_multipliers=wl.multipliers, prn_mode="bf16", prn_modes_allocated=("bf16",))
+    outs = []
+    for env in ({}, {"MPN_FC2_PAIRS": "0", "MPN_NO_PDL": "1"}):
+        for k in ("MPN_FC2_PAIRS", "MPN_NO_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        det = Detector(prn_weights, DetectorConfig(**cfg))
+        try:
+            side = torch.cuda.Stream()
+            dev_in = [_cuda(inp[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")]
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # second call = graph replay
+                    o = det.run_device(*dev_in)
+            side.synchronize()
+            outs.append({k: v.cpu().numpy().copy() for k, v in o.items()})
+        finally:
+            det.close()
+    n = int(outs[0]["person_offsets"][-1])
+    assert n > 256
+    for k in outs[0]:
+        rows = n if k in ("keypoint_scores", "keypoint_positions") else None
+        assert_bit_equal(outs[1][k][:rows], outs[0][k][:rows], k)
+
+
 def test_prn_known_answers(prn_weights):
     """detector/prn.py:24: zero weights -> output == input; large negative b2 -> ReLU clamps -> output == input."""
     from multiposenet_b200 import Detector, DetectorConfig
