@@ -503,6 +503,30 @@ def test_full_path_c2_bf16(det9, prn_weights):
     _full_case(det9, wl, synthetic.make_inputs(wl, batch=2), prn_weights, "bf16", True)
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_full_path_with_no_person_at_all(det6, prn_weights, mode):
+    """Nothing confident in any image: zero persons flow through crop / PRN / decode (every grid exits on the device-side
+    count, the cooperative PRN kernel included), the seven outputs keep their contract, and the handle is fine for the
+    next, normal call (counters re-armed, in-place buffers untouched)."""
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    cold = dict(inp, class_logits=np.full_like(inp["class_logits"], -9.0))
+    dev = [_cuda(cold[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")]
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):                               # direct launches + capture, then graph replay
+            out = det6.run_device(*dev, score_threshold=wl.score_threshold, iou_threshold=wl.iou_threshold,
+                                  max_boxes=wl.max_detections, prn_mode=mode)
+    side.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    assert (got["num_boxes"] == 0).all() and (got["person_offsets"] == 0).all()
+    assert not got["boxes"].any() and not got["scores"].any()
+    want_kh, want_seg, _, _ = oracle.heatmaps(cold["heatmap_logits"])
+    assert_bit_equal(got["keypoint_heatmaps"], want_kh, "keypoint_heatmaps")
+    assert_bit_equal(got["segmentation_masks"], want_seg, "segmentation_masks")
+    _full_case(det6, wl, inp, prn_weights, mode, host=False)
+
+
 def test_host_pipeline_pinned_inputs_three_in_flight(det6, prn_weights):
     """mpn_submit_host / mpn_wait with pinned inputs (box codes gathered in place over PCIe, never copied) and three
     calls in flight give the same bits as one call at a time with pageable inputs (staged copies)."""
