@@ -24,7 +24,7 @@ namespace mpn {
 
 namespace {
 
-constexpr int kNmsThreads = 512;
+constexpr int kWideNmsAbove = 64;      // max_detections above this: 1024-thread sort / NMS CTAs
 
 struct Anchor { float ymin, xmin, ymax, xmax; };
 
@@ -196,25 +196,29 @@ __device__ __forceinline__ void person_list(const DetectArgs &a, int *s_off)
 //           candidates -> first live one -> everybody tests itself against that box
 //      until max_detections boxes are kept or the candidates run out.  TensorFlow's NonMaxSuppressionV3 semantics:
 //      strict `IoU > thr`, kept boxes in descending score order.
-constexpr int kChunk = 512;
-constexpr int kMaskWords = kChunk / 32;
-constexpr int kRankSortCap = 1024;
+// T threads per CTA: 512 by default; 1024 for calls that may keep many boxes per image (crowded scenes: thousands of
+// candidates per image, where the candidate-versus-kept tests and the sort dominate and one CTA per image is all the
+// parallelism there is).  Chunk = one candidate per thread, rank sort for up to two keys per thread.
 
+template <int T>
 struct NmsSmem {
+    static constexpr int kChunk = T, kMaskWords = T / 32, kRankSortCap = 2 * T;
     unsigned long long keys[kSortSmemCap];     // 64 KB: unsorted (rank sort source) or bitonic work area
-    unsigned long long sorted[kRankSortCap];   //  8 KB: rank sort destination
-    float4 box[kChunk];                        //  8 KB: decoded boxes of the current chunk
-    NmsBox nbox[kChunk];                       // 10 KB: ... with ordered corners and area (pair tests)
+    unsigned long long sorted[kRankSortCap];   //  8 / 16 KB: rank sort destination
+    float4 box[kChunk];                        //  8 / 16 KB: decoded boxes of the current chunk
+    NmsBox nbox[kChunk];                       // 10 / 20 KB: ... with ordered corners and area (pair tests)
     NmsBox kept_nbox[kMaxDetCap];              // 20 KB
     int kept_local[kChunk];                    //  2 KB: chunk-local indices kept by step d
     unsigned alive[2][kMaskWords];             // live-candidate ballots, double buffered
     int n_kept;                                // boxes kept by the current chunk
 };
 
-__global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
+template <int T>
+__global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
 {
+    constexpr int kNmsThreads = T, kChunk = T, kMaskWords = T / 32, kRankSortCap = 2 * T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NmsSmem &sm = *reinterpret_cast<NmsSmem *>(smem_raw);
+    NmsSmem<T> &sm = *reinterpret_cast<NmsSmem<T> *>(smem_raw);
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     pdl_wait();                                        // the candidate scan has completed
@@ -376,7 +380,9 @@ int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
 // per device, at handle creation: the sort / NMS kernel needs more than the default 48 KB of dynamic shared memory
 int detect_prepare()
 {
-    const cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem<512>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sort_nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem<1024>));
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
@@ -397,7 +403,10 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cud
     ++launches;
     if (after_candidates) cudaEventRecord(after_candidates, s);
     prof_mark(s, "sort_nms");
-    launch_k(sort_nms_kernel, dim3(a.B), dim3(kNmsThreads), sizeof(NmsSmem), s, true, t, a);
+    if (a.max_det > kWideNmsAbove)
+        launch_k(sort_nms_kernel<1024>, dim3(a.B), dim3(1024), sizeof(NmsSmem<1024>), s, true, t, a);
+    else
+        launch_k(sort_nms_kernel<512>, dim3(a.B), dim3(512), sizeof(NmsSmem<512>), s, true, t, a);
     ++launches;
     return launches;
 }
