@@ -639,8 +639,15 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
         rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
                                          nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
     if (rc) return rc;
-    // crop sizes the padded-map kernel does not cover fall back to per-tap normalisation of the 17-channel map
-    const bool padded = crop_padded_supported(h->cfg.crop_height, h->cfg.crop_width);
+    // Two ways to the normalised taps: normalise the WHOLE map once into a padded workspace and crop from that (one
+    // division per heatmap value, 16-byte tap loads), or crop from keypoint_heatmaps and normalise every tap (4 divisions
+    // per crop sample, scalar tap loads, but no pass over the map).  Large maps with few persons take the second way
+    // (1024 x 1024 x 64 with <= 25 boxes per image: 667 -> 507 us per call), everything else the first (crowded 640 x 640
+    // x 32: 887 against 1134 us; one 512 x 512 image: 58.3 against 62.4 us); so do crop sizes the padded kernel does
+    // not cover.
+    const long long map_pixels = (long long)in->batch * (in->height / h->cfg.downsample) * (in->width / h->cfg.downsample);
+    const bool per_tap = map_pixels > 1500LL * in->batch * p->max_detections;
+    const bool padded = crop_padded_supported(h->cfg.crop_height, h->cfg.crop_width) && !per_tap;
     if (!(skip & 4u) && padded)
         rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
     if (rc) return rc;

@@ -235,10 +235,24 @@ __global__ void __launch_bounds__(kHeadPix) heatmap_head_kernel(const float *__r
     publish_minmax(s_min, s_max, &s_last, partial, counter, minmax);
 }
 
-// create_pb.py:93-94 on one tap
-__device__ __forceinline__ float normalise_tap(float v, float m, float M, float mask)
+// Division by a channel's constant range d = M - m (create_pb.py:93), one per heatmap value or crop tap -- the kernels
+// that do it are bound by instruction issue.  With y = RN(1 / d) and q = RN(a y), the correction
+// q' = fma(fma(-q, d, a), y, q) IS the correctly rounded a / d for 0 <= a <= d, d >= 2^-60 and a == 0 or a >= 1e-30
+// (tools/div_check.cu: 10^10 pairs incl. the all-ones / all-zeros mantissas, 0 mismatches; subnormal a does differ).
+// range_rcp() returns 0 for a range that must take the true division (tiny, NaN, or M == m, whose 0 / 0 = NaN the
+// reference propagates).
+__device__ __forceinline__ float range_rcp(float d) { return (d >= 8.67361738e-19f) ? __frcp_rn(d) : 0.0f; }   // 2^-60
+__device__ __forceinline__ float div_by_range(float a, float d, float y)
 {
-    return fmul(fdiv(fsub(v, m), fsub(M, m)), mask);
+    if (y == 0.0f || (a != 0.0f && a < 1e-30f)) return fdiv(a, d);
+    const float q0 = fmul(a, y);
+    return __fmaf_rn(__fmaf_rn(-q0, d, a), y, q0);
+}
+
+// create_pb.py:93-94 on one tap
+__device__ __forceinline__ float normalise_tap(float v, float m, float d, float y, float mask)
+{
+    return fmul(div_by_range(fsub(v, m), d, y), mask);
 }
 
 // create_pb.py:93-94 over the whole map: nh = (kh - m) / (M - m) * float(M > 0.2).  Normalising every heatmap pixel once
@@ -262,11 +276,7 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict_
         s_m[threadIdx.x] = m;
         s_d[threadIdx.x] = d;
         s_mask[threadIdx.x] = (real && M > 0.2f) ? 1.0f : 0.0f;
-        // Division by the channel's constant range, one IEEE division per heatmap value (the kernel is issue bound on it):
-        // with y = RN(1 / d), q = RN(a y), the correction q' = fma(fma(-q, d, a), y, q) IS the correctly rounded a / d
-        // for 0 <= a <= d, d >= 2^-60 and a == 0 or a >= 1e-30 (tools/div_check.cu: 10^10 pairs incl. the all-ones /
-        // all-zeros mantissas, 0 mismatches; subnormal a does differ).  0 marks a channel that takes the true division.
-        s_rcp[threadIdx.x] = (d >= 8.67361738e-19f) ? __frcp_rn(d) : 0.0f;      // 2^-60; false for NaN and for M == m
+        s_rcp[threadIdx.x] = range_rcp(d);
     }
     __syncthreads();
     const float *src = kh + (size_t)img * npix * kNK;
@@ -279,15 +289,7 @@ __global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict_
         for (int k = 0; k < 4; ++k) {
             const int c = 4 * g + k;
             const float v = c < kNK ? __ldcg(src + (size_t)p * kNK + c) : 0.0f;
-            const float a = fsub(v, s_m[c]), y = s_rcp[c];
-            float q;
-            if (y == 0.0f || (a != 0.0f && a < 1e-30f)) {
-                q = fdiv(a, s_d[c]);
-            } else {
-                const float q0 = fmul(a, y);
-                q = __fmaf_rn(__fmaf_rn(-q0, s_d[c], a), y, q0);
-            }
-            o[k] = c < kNK ? fmul(q, s_mask[c]) : 0.0f;
+            o[k] = c < kNK ? normalise_tap(v, s_m[c], s_d[c], s_rcp[c], s_mask[c]) : 0.0f;
         }
         dst[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
                                                    float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
 {
     __shared__ PixTab s_tab[kCropMaxPix];
-    __shared__ float s_m[kNK], s_M[kNK], s_mask[kNK];
+    __shared__ float s_m[kNK], s_d[kNK], s_rcp[kNK], s_mask[kNK];
     pdl_trigger();
     pdl_wait();
     const int n = blockIdx.x;
@@ -433,7 +435,9 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
     if (minmax != nullptr && threadIdx.x < kNK) {
         const float m = __ldg(minmax + ((size_t)b * kNK + threadIdx.x) * 2);
         const float M = __ldg(minmax + ((size_t)b * kNK + threadIdx.x) * 2 + 1);
-        s_m[threadIdx.x] = m; s_M[threadIdx.x] = M; s_mask[threadIdx.x] = (M > 0.2f) ? 1.0f : 0.0f;
+        const float d = fsub(M, m);
+        s_m[threadIdx.x] = m; s_d[threadIdx.x] = d; s_rcp[threadIdx.x] = range_rcp(d);
+        s_mask[threadIdx.x] = (M > 0.2f) ? 1.0f : 0.0f;
     }
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {
         const int cy = cy0 + p / crop_w, cx = p % crop_w;
@@ -477,9 +481,9 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
                 float tl = __ldg(q + t.top + t.left), tr = __ldg(q + t.top + t.right);
                 float bl = __ldg(q + t.bot + t.left), br = __ldg(q + t.bot + t.right);
                 if (norm) {
-                    const float m = s_m[c], M = s_M[c], mask = s_mask[c];
-                    tl = normalise_tap(tl, m, M, mask); tr = normalise_tap(tr, m, M, mask);
-                    bl = normalise_tap(bl, m, M, mask); br = normalise_tap(br, m, M, mask);
+                    const float m = s_m[c], d = s_d[c], y = s_rcp[c], mask = s_mask[c];
+                    tl = normalise_tap(tl, m, d, y, mask); tr = normalise_tap(tr, m, d, y, mask);
+                    bl = normalise_tap(bl, m, d, y, mask); br = normalise_tap(br, m, d, y, mask);
                 }
                 const float tp = fadd(tl, fmul(fsub(tr, tl), t.lx));
                 const float bt = fadd(bl, fmul(fsub(br, bl), t.lx));
