@@ -178,6 +178,7 @@ int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *b
             return fail(h, MPN_ERR_INVALID_ARGUMENT, "encoded_boxes must be 16-byte aligned");
         a.cls = in->class_logits;
         a.enc = in->encoded_boxes;
+        a.enc_ind = h->enc_indirect;
     } else {
         for (int i = 0; i < t.n_levels; ++i) {
             if (!in->level_class[i] || !in->level_boxes[i])
@@ -422,7 +423,8 @@ void mpn_destroy(mpn_handle *h)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (HostSlot &sl : h->slots) {
-        void *sp[] = {sl.cls, sl.enc, sl.hml, sl.kh, sl.seg, sl.boxes, sl.scores, sl.kscores, sl.kpos, sl.num, sl.offsets};
+        void *sp[] = {sl.cls, sl.enc, sl.hml, sl.kh, sl.seg, sl.boxes, sl.scores, sl.kscores, sl.kpos, sl.num, sl.offsets,
+                      (void *)sl.enc_word};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
@@ -685,7 +687,9 @@ static void make_graph_key(const mpn_handle *h, const mpn_inputs *in, const mpn_
 {
     memset(k, 0, sizeof(*k));
     k->v[0] = (uint64_t)in->batch; k->v[1] = (uint64_t)in->height; k->v[2] = (uint64_t)in->width;
-    k->v[3] = (uint64_t)(uintptr_t)in->class_logits; k->v[4] = (uint64_t)(uintptr_t)in->encoded_boxes;
+    k->v[3] = (uint64_t)(uintptr_t)in->class_logits;
+    // host calls read the box codes through a per-slot device word: the graph does not depend on the caller's buffer
+    k->v[4] = h->enc_indirect ? (uint64_t)(uintptr_t)h->enc_indirect : (uint64_t)(uintptr_t)in->encoded_boxes;
     k->v[5] = (uint64_t)(uintptr_t)in->heatmap_logits;
     const bool levels = !(in->class_logits && in->encoded_boxes) && in->level_class && in->level_boxes;
     for (int i = 0; i < h->cfg.num_levels && levels; ++i) {
@@ -854,7 +858,14 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
         h->last_h2d_bytes += (int64_t)(B * A * 16);
     }
     MPN_CUDA(h, cudaEventRecord(sl.ev_in, si));
-    // ---- the path on the compute stream
+    // ---- the path on the compute stream.  The kernels find this call's box codes through a per-slot device word, so
+    // that ONE captured graph per slot serves every buffer the caller passes (a graph keyed on the caller's pointer was
+    // re-captured for every new pinned buffer: 0.28 instead of 0.07 ms per single-image call over a ring of 91 buffers).
+    // The word is written on the compute stream BEFORE it waits for the copies: the copy-in stream carries nothing but
+    // copies (a kernel between them cost 5 % of the PCIe-bound throughput).
+    if (!sl.enc_word) MPN_CUDA(h, dalloc(&sl.enc_word, 1));
+    if (launch_set_pointer(sl.enc_word, enc, sc) < 0 || cudaPeekAtLastError() != cudaSuccess)
+        return fail(h, MPN_ERR_CUDA, "host path: %s", cudaGetErrorString(cudaGetLastError()));
     MPN_CUDA(h, cudaStreamWaitEvent(sc, sl.ev_in, 0));
     mpn_inputs din = *in;
     din.class_logits = sl.cls; din.encoded_boxes = enc; din.heatmap_logits = sl.hml;
@@ -863,7 +874,9 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
     dout.boxes = sl.boxes; dout.scores = sl.scores; dout.num_boxes = sl.num;
     dout.keypoint_heatmaps = sl.kh; dout.segmentation_masks = out->segmentation_masks ? sl.seg : nullptr;
     dout.keypoint_scores = sl.kscores; dout.keypoint_positions = sl.kpos; dout.person_offsets = sl.offsets;
+    h->enc_indirect = sl.enc_word;
     rc = mpn_run(h, &din, p, &dout, sc);
+    h->enc_indirect = nullptr;
     if (rc) return rc;
     MPN_CUDA(h, cudaEventRecord(sl.ev_comp, sc));
     // ---- fetch (inference/detector.py:48) on the copy-out stream

@@ -37,6 +37,8 @@ struct LevelPtrs {
 struct DetectArgs {
     const float *cls;        // [B, A] or NULL
     const float *enc;        // [B, A, 4] or NULL
+    const float *const *enc_ind;   // host path: device word holding the box-code pointer of this call (NULL: use enc), so
+                                   // that one captured graph serves every pinned buffer the caller passes
     LevelPtrs lv;            // used when cls == NULL
     int B;
     float thr, iou_thr, pre_thr;
@@ -106,6 +108,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // ---- launchers (each returns the number of kernels it launched, or a negative cudaError) ----
 int detect_prepare();   // once per device (handle creation)
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s);
+int launch_set_pointer(const float **slot, const float *value, cudaStream_t s);     // *slot = value, stream-ordered
 // after_candidates (optional): event recorded on `s` between the candidate scan and the sort / NMS kernel
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates = nullptr);
 

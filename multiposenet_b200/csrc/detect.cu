@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(256) candidates_nchw_kernel(const AnchorTable 
 __device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectArgs &a, int img, int anchor, int l,
                                             int loc, int k)
 {
-    if (a.enc) return __ldg(reinterpret_cast<const float4 *>(a.enc) + (size_t)img * t.num_anchors + anchor);
+    if (a.enc) {
+        const float *enc = a.enc_ind ? reinterpret_cast<const float *>(__ldcg(reinterpret_cast<const unsigned long long *>(a.enc_ind)))
+                                     : a.enc;
+        return __ldg(reinterpret_cast<const float4 *>(enc) + (size_t)img * t.num_anchors + anchor);
+    }
     const int plane = t.gh[l] * t.gw[l];
     const float *p = a.lv.box[l] + ((size_t)img * t.n_loc * 4 + (size_t)k * 4) * plane + loc;   // channel k*4+coord
     return make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane), __ldg(p + 3 * plane));
@@ -369,7 +373,15 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
     }
 }
 
+__global__ void set_pointer_kernel(const float **slot, const float *value) { *slot = value; }
+
 }  // namespace
+
+int launch_set_pointer(const float **slot, const float *value, cudaStream_t s)
+{
+    set_pointer_kernel<<<1, 1, 0, s>>>(slot, value);
+    return 1;
+}
 
 int launch_anchors(const AnchorTable &t, float *out, cudaStream_t s)
 {

@@ -7,6 +7,7 @@ constexpr int kHostSlots = 3;
 // Device staging of one in-flight host call.
 struct HostSlot {
     float *cls, *enc, *hml, *kh, *seg, *boxes, *scores, *kscores, *kpos;
+    const float **enc_word;      // device word: where this call's box codes are (slot copy or the caller's pinned buffer)
     int *num, *offsets;
     cudaEvent_t ev_in, ev_comp, ev_out;
     bool used;
@@ -36,6 +37,7 @@ struct mpn_handle {
     uint64_t graph_clock;
     int graph_miss_streak;  // consecutive calls that had to capture: callers that never repeat a description get direct launches
     bool cfg_use_graphs, graphs_disabled;
+    const float *const *enc_indirect;   // set around the mpn_run of a host call (see DetectArgs::enc_ind)
     bool use_pdl;           // programmatic dependent launch between consecutive kernels of a branch
     unsigned debug_skip;    // mpn_debug_skip: bit i set = stage i is not launched (timing experiments only)
     // detect workspace
