@@ -228,7 +228,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             stamp(args, 1);                                                 // all fc1 loads issued
             // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces.
-            // Measured and not kept (profiles/r01e_summary.md): TMA L2 prefetches of the rest of the W2 tile issued here
+            // Measured and not kept (profiles/r01f_summary.md): TMA L2 prefetches of the rest of the W2 tile issued here
             // or after barrier 1, a sliding L2 prefetch window ahead of the ring in both layers, an L2 prefetch of W1
             // from a kernel in the front half of the call, and a per-CTA rotation of the k order.  With W2 L2-resident
             // phase 3 got only 1.1 us shorter: both streaming phases move ~97 MB (70 MB of weights + the activation
