@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
         const float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float sa = exact_sigmoidf(va[j]), sb = exact_sigmoidf(vb[j]);
+            float sa, sb;
+            exact_sigmoidf_pair(va[j], vb[j], sa, sb);      // two tiles' values share the packed FFMA2 / FMUL2 stream
             mn[j] = fminf(mn[j], sa); mx[j] = fmaxf(mx[j], sa);
             if (two) { mn[j] = fminf(mn[j], sb); mx[j] = fmaxf(mx[j], sb); }
             if (dst[j]) {

@@ -125,11 +125,17 @@ __device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], i
     const float m2 = m == -__int_as_float(0x7f800000) ? 0.0f : -m * kLog2e;    // empty partial: keep the exponents at -inf
     float s = 0.0f;
     unsigned hits = 0u;                                // bit i: exact_expf(v[i] - m) == 1.0f
+    const f32x2 mm = f2_bcast(m), l2e = f2_bcast(kLog2e), mm2 = f2_bcast(m2);
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-        const float d = fsub(v[i], m);
-        hits |= (d >= x0) ? (1u << i) : 0u;
-        s = fadd(s, exp2f_approx(fmaf(v[i], kLog2e, m2)));
+    for (int i = 0; i < kMaxPerThread; i += 2) {       // two logits per FADD2 / FFMA2, same operations and order per lane
+        const f32x2 vv = f2_pack(v[i], v[i + 1]);
+        float d0, d1, t0, t1;
+        f2_unpack(f2_sub(vv, mm), d0, d1);
+        f2_unpack(f2_fma(vv, l2e, mm2), t0, t1);
+        hits |= (d0 >= x0) ? (1u << i) : 0u;
+        hits |= (d1 >= x0) ? (2u << i) : 0u;
+        s = fadd(s, exp2f_approx(t0));
+        s = fadd(s, exp2f_approx(t1));
     }
     const int me = q * kNK + c;                        // == threadIdx.x
     sc.m[me] = m; sc.s[me] = s; sc.hits[me] = (unsigned short)hits;
