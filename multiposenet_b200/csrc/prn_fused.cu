@@ -13,12 +13,14 @@
 //   phase 2  split-K reduce in fixed order + bias + ReLU + bf16 -> y1 (deterministic, no atomics on data)
 //   barrier
 //   phase 3  fc2: CTA t owns 240 output columns (143 tiles); A = y1 (L2-resident), B = W2 tile;
-//            epilogue logits = x + relu(acc + b2)
+//            epilogue logits = x + relu(acc + b2): in place (logits == x, how mpn_run calls it) as a TMA reduce-add of
+//            relu(acc + b2) into x, performed in L2; out of place by loading x
 // The producer warp runs ahead: while the CTA sits in the barriers / the reduce it is already pulling its first W2
-// tiles into the ring, so HBM stays busy across the phase boundaries.
+// tiles into the ring, so HBM stays busy across the phase boundaries.  Under programmatic dependent launch the prologue
+// and the first three W1 boxes are under way before the crop kernel has finished.
 //
-// Roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) + TMEM allocation, warps 2..9 =
-// epilogue / reduce (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// Roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) + TMEM allocation, warps 2..17 =
+// epilogue / reduce (TMEM lane quadrant = warp % 4, column group = (warp - 2) / 4).
 // Activations are fetched as 16-row TMA boxes, only as many as there are persons (M is fixed at 128 per MMA but
 // rows past the last box are never loaded; their accumulator rows are garbage and never stored).
 #include <cuda.h>
