@@ -123,3 +123,21 @@ def test_world_size_2_gloo_gather(tmp_path):
     # persons stay in image order: the marker written by rank 1 comes after rank 0's rows
     n0 = int(parts[0]["num_boxes"].sum())
     assert (m["keypoint_scores"][:n0] == 0.0).all() and (m["keypoint_scores"][n0:] == 4.0).all()
+
+
+def test_bench_and_tools_compile_and_bench_formulas_hold():
+    """bench.py and the development tools at least parse; the algorithmic byte counts of DESIGN.md (section 4) are what
+    bench.py's roofline uses."""
+    import glob
+    import py_compile
+    for path in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + \
+            sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
+        py_compile.compile(path, doraise=True)
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = synthetic.WORKLOADS["c2"]
+    D, Hd = 56 * 36 * 17, 1024
+    assert bench.algorithmic_bytes("prn_fused", wl, 8, 77, 1825, "bf16") == 2 * D * Hd * 2 + 77 * D * 10
+    assert bench.algorithmic_bytes("prn_fused", wl, 32, 2805, 66877, "bf16") is None      # idle above 256 persons
+    assert bench.algorithmic_bytes("heatmap", wl, 8, 77, 1825, "bf16") == 2 * 72 * 160 * 160 * 8
+    assert bench.algorithmic_bytes("keypoint_decode", wl, 8, 77, 1825, "bf16") == 77 * D * 4
