@@ -10,7 +10,9 @@ collective on the data path, so scaling is "weak" and `va
 divided by the slowest rank's device time.
 
 Legs (all in one run, one JSON line on rank 0):
-  value      inputs already resident in HBM, outputs left in HBM; K steps back to back on one stream, CUDA events.
+  value      inputs already resident in HBM, outputs left in HBM; K steps fed round-robin to --lanes Detector handles
+             (default 3, each on its own stream: neighbouring batches overlap), CUDA events around the K steps; the same
+             K steps back to back on ONE handle and stream are reported beside it (`single_lane`).
              Inputs rotate over a ring of distinct batches whose total size exceeds the 126 MB L2 (no flush needed).
   e2e        the same steps through the reference-facing call with HOST buffers: pinned host -> device copies of
              the step's inputs, the path, and device -> host copies of all seven outputs (heatmaps included, as
@@ -61,6 +63,8 @@ def parse_args():
     ap.add_argument("--prn-mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="Detector handles / CUDA streams fed round-robin in the device-resident leg (DetectorLanes)")
     return ap.parse_args()
 
 
@@ -227,7 +231,8 @@ def config_dict(wl, args, ring_sets):
             "anchors_per_location": wl.n_loc, "anchors_per_image": wl.num_anchors,
             "score_threshold": wl.score_threshold, "iou_threshold": wl.iou_threshold,
             "max_detections": wl.max_detections, "prn": args.prn_mode, "parallelism": f"dp{args.gpus} (image-sharded, no collective)",
-            "l2": f"inputs rotate over {ring_sets} distinct batches (> 126 MB L2 in total), no flush"}
+            "l2": f"inputs rotate over {ring_sets} distinct batches (> 126 MB L2 in total), no flush",
+            "lanes": f"{max(1, getattr(args, 'lanes', 1))} Detector handle(s), one CUDA stream each, batches fed round-robin"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU legs
@@ -244,7 +249,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from multiposenet_b200 import Detector, DetectorConfig
+    from multiposenet_b200 import DetectorConfig, DetectorLanes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
@@ -260,10 +265,13 @@ def main():
 
     K, Wm = args.steps, max(args.warmup, 3)
     weights = synthetic.make_prn_weights()
-    det = Detector(weights, DetectorConfig(
+    n_lanes = max(1, args.lanes)
+    lanes = DetectorLanes(weights, DetectorConfig(
         max_batch=wl.batch, max_height=wl.height, max_width=wl.width, max_boxes=wl.max_detections,
         score_threshold=wl.score_threshold, iou_threshold=wl.iou_threshold, scale_multipliers=wl.multipliers,
-        aspect_ratios=wl.ratios, prn_mode=args.prn_mode, prn_modes_allocated=(args.prn_mode,), device=local_rank))
+        aspect_ratios=wl.ratios, prn_mode=args.prn_mode, prn_modes_allocated=(args.prn_mode,), device=local_rank),
+        lanes=n_lanes)
+    det = lanes.detectors[0]            # the single-lane, e2e and profiling legs run on this handle
 
     probe = synthetic.make_inputs(wl, replicate=100 * rank)
     n_sets = max(2, -(-int(1.3 * L2_BYTES) // set_bytes(probe)))
@@ -280,15 +288,24 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---- leg 1: device-resident ------------------------------------------------------------------------------
-    # on a side stream: the library replays one CUDA graph per distinct (inputs, outputs) description there (the
+    # on side streams: the library replays one CUDA graph per distinct (inputs, outputs) description there (the
     # legacy default stream cannot be captured)
     side = torch.cuda.Stream(device=dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # (a) one handle, one stream: K calls back to back
     torch.cuda.synchronize()
     with torch.cuda.stream(side):
         for i in range(max(Wm, n_sets)):
             out = dev_step(i)
     barrier()
-    _, launches0 = det.launch_count()
+    launches0 = lanes.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     with torch.cuda.stream(side):
@@ -300,18 +317,44 @@ def main():
     t1 = time.time()
     if sampler:
         sampler.mark(t0, t1)
-    _, launches1 = det.launch_count()
-    n_launches = int(launches1 - launches0)
+    n_launches = int(lanes.launch_count() - launches0)
+    single_ms = max_over_ranks(e0.elapsed_time(e1))
+    persons = int(out["person_offsets"][-1].item())
+
+    # (b) the K steps fed round-robin to the lanes; the events sit on `side`, every lane starts after e0 and `side`
+    # waits for every lane before e1
+    def lane_step(i):
+        s = dev_ring[i % n_sets]
+        return lanes.submit(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], (wl.height, wl.width))
+
+    dev_ms = single_ms
+    if n_lanes > 1:
+        with torch.cuda.stream(side):
+            lanes.fork()
+            for i in range(max(Wm, n_sets * n_lanes)):      # every lane sees every input set once (graph capture)
+                lane_step(i)
+            lanes.join()
+        barrier()
+        launches0 = lanes.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        with torch.cuda.stream(side):
+            e0.record()
+            lanes.fork(e0)
+            for i in range(K):
+                lane_step(Wm + i)
+            lanes.join()
+            e1.record()
+        barrier()
+        t1 = time.time()
+        if sampler:
+            sampler.mark(t0, t1)
+        n_launches = int(lanes.launch_count() - launches0)
+        dev_ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
         t = torch.tensor([n_launches], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         n_launches = int(t.item())
-    dev_ms = e0.elapsed_time(e1)
-    persons = int(out["person_offsets"][-1].item())
-    if world > 1:
-        t = torch.tensor([dev_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
 
     # ---- leg 2: end to end through host buffers --------------------------------------------------------------
     # every step copies its inputs from pinned host memory, runs the path and copies all seven outputs back; up to
@@ -403,14 +446,17 @@ def main():
         if top == "prn_fused":
             # the dominant kernel alone: K replays of a graph that contains only this kernel (every other stage skipped,
             # its inputs -- the crops of the last full step -- stay in place), CUDA events on the launching stream
+            # (the skipped stages are the only readers of the rotating inputs, so a few sets are enough: a workload with
+            # a long input ring would otherwise spend this pass capturing one new graph per set)
             det.debug_skip(1 | 2 | 4 | 8 | 32)
+            m_sets = min(n_sets, 7)
             with torch.cuda.stream(side):
-                for i in range(10):
-                    dev_step(i)
+                for i in range(max(10, m_sets)):
+                    dev_step(i % m_sets)
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
                 for i in range(min(K, 200)):
-                    dev_step(i)
+                    dev_step(i % m_sets)
                 p1.record()
             torch.cuda.synchronize()
             det.debug_skip(0)
@@ -429,7 +475,7 @@ def main():
         res = run_cpu_leg(wl, weights, ring, seconds=args.cpu_seconds)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    det.close()
+    lanes.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -438,7 +484,10 @@ def main():
     images = B * K * world
     line = {
         "metric": METRIC, "value": images / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / K, "lanes": n_lanes,
+        "single_lane": {"value": images / (single_ms / 1e3), "unit": UNIT, "ms_per_step": single_ms / K,
+                        "note": "the same K steps back to back on one handle and one stream"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (decode/NMS/crop/softmax) + " + ("bf16 tcgen05, f32 accumulate (PRN)" if args.prn_mode == "bf16" else "f32 (PRN)"),
         "data": "synthetic", "config": config_dict(wl, args, n_sets),
         "e2e": {"value": images / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

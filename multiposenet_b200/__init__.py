@@ -8,7 +8,7 @@ decode) as hand-written sm_100a CUDA kernels behind a C ABI (include/mpn_b200.h)
 Importing the package does not load the CUDA library; constructing a Detector does,
 and raises if the library or a B200 is missing (there is no CPU fallback).
 """
-__all__ = ["Detector", "DetectorConfig", "OUTPUT_NAMES"]
+__all__ = ["Detector", "DetectorConfig", "DetectorLanes", "OUTPUT_NAMES"]
 
 
 def __getattr__(name):

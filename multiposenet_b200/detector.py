@@ -479,3 +479,54 @@ class Detector:
         last, total = C.c_int64(0), C.c_int64(0)
         self._lib.mpn_launch_count(self._handle, C.byref(last), C.byref(total))
         return last.value, total.value
+
+
+class DetectorLanes:
+    """Throughput mode for a stream of device-resident batches: `lanes` Detector handles on one GPU, each with its own
+    CUDA stream, fed round-robin.  Calls of neighbouring batches overlap: the latency-bound front half of one call
+    (candidate scan, sort / NMS, heatmap pass) and its keypoint decode run beside another call's kernels instead of
+    leaving the device to one short grid at a time.  The PRN kernel owns every SM while it runs, so the gain is bounded by
+    the time of the other six kernels (c2, per batch: 88.1 us alone, 81.6 with 2 lanes, 78.4 with 3, 78.1 with 6;
+    tools/two_streams.py).  Every lane is an
+    independent handle (own workspace and weight copy, 0.3 GB each), so results are those of a lone Detector, bit for
+    bit; a handle is not re-entrant (include/mpn_b200.h), the lanes are what makes concurrent calls legal."""
+
+    def __init__(self, prn_weights, config: Optional[DetectorConfig] = None, lanes: int = 2, device: Optional[int] = None):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.detectors = [Detector(prn_weights, config, device) for _ in range(lanes)]
+        self.device = self.detectors[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
+        self._next = 0
+
+    def __len__(self):
+        return len(self.detectors)
+
+    def fork(self, event=None):
+        """Every lane waits for `event` (default: everything submitted so far to the caller's current stream)."""
+        if event is None:
+            event = torch.cuda.current_stream(self.device).record_event()
+        for st in self.streams:
+            st.wait_event(event)
+
+    def submit(self, encoded_boxes, class_logits, heatmap_logits, image_hw=None, **kwargs):
+        """run_device on the next lane's stream; returns (lane index, that lane's output dict).  The dict is reused by the
+        lane's next call: consume it (on that lane's stream, or after join()) before `lanes` more submits."""
+        lane = self._next
+        self._next = (lane + 1) % len(self.detectors)
+        with torch.cuda.stream(self.streams[lane]):
+            out = self.detectors[lane].run_device(encoded_boxes, class_logits, heatmap_logits, image_hw, **kwargs)
+        return lane, out
+
+    def join(self):
+        """The caller's current stream waits for every lane."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def launch_count(self):
+        return sum(d.launch_count()[1] for d in self.detectors)
+
+    def close(self):
+        for d in self.detectors:
+            d.close()

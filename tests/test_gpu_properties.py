@@ -185,3 +185,40 @@ def test_1024_image_batch_of_8(weights):
         _eq(r["keypoint_positions"][:hi - lo], full["keypoint_positions"][lo:hi], "1024 keypoints of a single image")
     finally:
         det.close()
+
+
+def test_lanes_interleaved_calls_reproduce_the_lone_detector(det_c2, weights):
+    """DetectorLanes: batches fed round-robin to 3 handles on 3 streams, many calls in flight at once (cooperative PRN
+    kernels of different handles queue behind each other), every result bit-identical to the same batch through one
+    handle alone."""
+    from multiposenet_b200 import DetectorConfig, DetectorLanes
+    wl = synthetic.WORKLOADS["c2"]
+    sets = [synthetic.make_inputs(wl, replicate=r) for r in range(4)]
+    alone = [_run(det_c2, s) for s in sets]
+    dev = [{k: _cuda(s[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")} for s in sets]
+    lanes = DetectorLanes(weights, DetectorConfig(max_batch=8, max_height=640, max_width=640, max_boxes=25,
+                                                  score_threshold=0.3, iou_threshold=0.5,
+                                                  scale_multipliers=wl.multipliers, prn_mode="bf16"), lanes=3)
+    try:
+        names = ("boxes", "scores", "num_boxes", "keypoint_scores", "keypoint_positions", "person_offsets",
+                 "keypoint_heatmaps", "segmentation_masks")
+        lanes.fork()
+        for rnd in range(6):                       # 24 calls queued without a host synchronisation
+            kept = []
+            for i, d in enumerate(dev):
+                lane, out = lanes.submit(d["encoded_boxes"], d["class_logits"], d["heatmap_logits"])
+                if rnd == 5:
+                    with torch.cuda.stream(lanes.streams[lane]):      # snapshot before the lane reuses its buffers
+                        kept.append((i, {k: out[k].clone() for k in names}))
+        lanes.join()
+        torch.cuda.synchronize()
+        assert len(kept) == len(sets)
+        for i, snap in kept:
+            n = int(alone[i]["person_offsets"][-1])
+            for k in names:
+                a, b = snap[k].cpu().numpy(), alone[i][k]
+                if k in ("keypoint_scores", "keypoint_positions"):
+                    a, b = a[:n], b[:n]            # rows past the person count are stale by contract
+                _eq(a, b, f"set {i}: {k}")
+    finally:
+        lanes.close()
