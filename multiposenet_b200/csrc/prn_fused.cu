@@ -8,7 +8,8 @@
 // tools/stream_bench.cu).  So the two layers are NOT two kernels: one CTA per SM stays resident and the weight stream
 // never stops --
 //   phase 1  fc1: CTA (hq, z) owns hidden quarter hq (256 units) and K split z of the 34272-long reduction;
-//            TMA ring -> tcgen05.mma 128 x 256 x 16 (accumulators in TMEM) -> fp32 partial sums to L2
+//            TMA ring -> tcgen05.mma, D[weight row, person] = W tile x activations: M = 128 weight rows (two MMAs per
+//            256-row tile), N = persons padded to 16, accumulators in TMEM -> fp32 partial sums to L2
 //   barrier  grid-wide (all CTAs are co-resident: cooperative launch)
 //   phase 2  split-K reduce in fixed order + bias + ReLU + bf16 -> y1 (deterministic, no atomics on data)
 //   barrier
@@ -19,10 +20,15 @@
 // tiles into the ring, so HBM stays busy across the phase boundaries.  Under programmatic dependent launch the prologue
 // and the first three W1 boxes are under way before the crop kernel has finished.
 //
+// The weights are the A operand and the persons the N dimension of the MMA, so everything that follows the weight
+// stream scales with the person count: MMA time (128 N / 256 cycles per instruction: 40 instead of 128 cycles at 80
+// persons), accumulator size (2 x N TMEM columns), TMEM drain (64 B / cycle / SM).  A TMEM lane then is a weight row,
+// i.e. a hidden unit / output column: 32 lanes of a warp are one 128-byte row segment of a person's row in global
+// memory, and the epilogues store (or TMA-reduce-add) straight from the accumulator layout, no transpose.
+//
 // Roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) + TMEM allocation, warps 2..17 =
-// epilogue / reduce (TMEM lane quadrant = warp % 4, column group = (warp - 2) / 4).
-// Activations are fetched as 16-row TMA boxes, only as many as there are persons (M is fixed at 128 per MMA but
-// rows past the last box are never loaded; their accumulator rows are garbage and never stored).
+// epilogue / reduce (TMEM lane quadrant = warp % 4; the four warps of a quadrant share its (half, 16-person chunk) items).
+// Activations are fetched as 16-row TMA boxes, only as many as there are persons.
 #include <cuda.h>
 
 #include <cstdio>
@@ -45,14 +51,15 @@ constexpr int kXBox = 16;                                // rows per activation 
 constexpr int kXBoxBytes = kXBox * 128;
 constexpr int kXTileBytes = 128 * 128;                   // one 128-row activation tile (16 KB)
 constexpr int kWTileBytes = 256 * 128;                   // one weight tile (32 KB; fc2 uses 240 of the 256 rows)
+constexpr int kWHalfBytes = 128 * 128;                   // one UMMA A operand: 128 weight rows
+constexpr int kAccCols = 256;                            // TMEM column of the second accumulator half
 constexpr int kRingBytes = 192 * 1024;                   // stage = [W tile | X tile 0 | X tile 1 (only for > 128 persons)]
 constexpr int kMaxStages = 4;                            //   <= 128 persons: 4 stages of 48 KB, else 3 stages of 64 KB
 constexpr int kEarly = 3;                                // W1 boxes requested before the person count is known
 constexpr int kEpiWarps = 16;                           // 4 per TMEM lane quadrant: the epilogues are issue-latency bound
 constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 32 x 16 fp32 transpose buffers
-constexpr int kB2Offset = kStgOffset + kEpiWarps * 2048; // b2 tile of the current fc2 output tile
-constexpr int kBarOffset = kB2Offset + 1024;
+constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 16 x 32 fp32 boxes of the in-place epilogue
+constexpr int kBarOffset = kStgOffset + kEpiWarps * 2048;
 constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 2) * 8 + 16 + 1024;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -78,7 +85,7 @@ struct FusedArgs {
 
 struct FusedMaps {
     CUtensorMap x, w1, y1, w2;
-    CUtensorMap out;           // fp32 chunk boxes over the buffer of the in-place call (re-encoded when it changes)
+    CUtensorMap out, out16;    // fp32 boxes (16 persons x 32 / 16 columns) over the buffer of the in-place call
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
@@ -139,13 +146,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 // kInPlace: logits == x (how mpn_run calls it).  The fc2 epilogue then never loads the residual: bias and ReLU are applied
-// in registers, the chunk goes to the warp's transpose buffer (a 64-byte-swizzled TMA box) and a TMA reduce-add performs
+// in registers, the 16-person x 32-column item goes to the warp's staging box (dense rows, no swizzle) and a TMA reduce-add performs
 // x += y2 in L2 -- the same single fp32 rounding, no residual registers, 4 B / element less L2 -> SM traffic.
 template <bool kInPlace>
 __global__ void __launch_bounds__(kThreads, 1)
 prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,
-                 const __grid_constant__ CUtensorMap tmap_out, const FusedArgs args)
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out16,
+                 const FusedArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
@@ -281,22 +289,25 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {   // ================= MMA issuer =================
-            constexpr uint32_t idesc1 = make_idesc_bf16(128, kFc1N);
-            constexpr uint32_t idesc2 = make_idesc_bf16(128, kFc2N);
+            // D[weight row, person] = W tile (A, M = 128, two halves of the 256-row tile) x activations (B, N = 16 nb):
+            // the accumulator holds one weight row per TMEM lane and one person per column, so its size, the MMA time
+            // (128 N / 256 cycles per instruction) and the TMEM drain all scale with the number of persons.
+            const uint32_t idesc = make_idesc_bf16(128, nb * kXBox);
             int it = 0, round = 0;
             if (has_fc1) {
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int st = it % n_stages;
                     mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
                     tc_fence_after();
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + st * kWTileBytes));
-                    const uint32_t x_addr = smem_u32(smem + x_base + st * x_stride);
-                    for (int m = 0; m < nm; ++m) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(x_addr + m * kXTileBytes);
+                    const uint32_t w_addr = smem_u32(smem + st * kWTileBytes);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + x_base + st * x_stride));
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                      idesc1, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar + st);
                 }
@@ -313,14 +324,17 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int st = it % n_stages;
                     mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
                     tc_fence_after();
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + st * kWTileBytes));
-                    const uint32_t x_addr = smem_u32(smem + x_base + st * x_stride);
-                    for (int m = 0; m < nm; ++m) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(x_addr + m * kXTileBytes);
+                    // rows 240..255 of the weight slot are not part of this tile (whatever the slot held before):
+                    // they only reach accumulator lanes 112..127 of the second half, which nobody reads
+                    const uint32_t w_addr = smem_u32(smem + st * kWTileBytes);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + x_base + st * x_stride));
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(m * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                      idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar + st);
                 }
@@ -331,38 +345,29 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
     } else {
         // ================= epilogue / reduce warps =================
-        // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule), column group cg = (warp - 2) / 4.  The work of these
-        // warps is short, serial and latency bound, hence many warps, 16-column chunks and addresses hoisted out of the
-        // chunk loops.
+        // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule); the four warps of a quadrant share its work items.
+        // A work item is (accumulator half m, 16-person chunk ch): 32 lanes = 32 consecutive weight rows (= 32 consecutive
+        // hidden units / output columns, i.e. one 128-byte row segment per person in global memory), 16 columns = 16
+        // persons.  No transpose: a warp-wide store of r[j] IS the coalesced row segment of person j.
         const int ew = warp - 2, q = warp & 3, cg = ew >> 2;
         const int tid_e = threadIdx.x - 64;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         float *stg = reinterpret_cast<float *>(smem + kStgOffset + ew * 2048);
-        float *s_b2 = reinterpret_cast<float *>(smem + kB2Offset);
-        const int sub_row = lane >> 2, sub_col = (lane & 3) << 2;    // coalesced side of the transpose
+        const int n_items = 2 * nb;
         int round = 0;
-        if (has_fc1) {   // ---- fc1 partial sums: partial[z][row][hq*256 + col]; this warp: columns [cg*64, +64) as 4 chunks
+        if (has_fc1) {   // ---- fc1 partial sums: partial[z][person][hq*256 + m*128 + q*32 + lane]
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
             if (tid_e == 0) stamp(args, 3);                                 // fc1 accumulators complete
-            for (int m = 0; m < nm; ++m) {
-                const int row0 = m * 128 + q * 32;
-                if (row0 >= N) break;                                       // warp-uniform: no person in these 32 rows
-                float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(row0 + sub_row) * args.hidden +
-                             hq * kFc1N + cg * 64 + sub_col;
-                const size_t row_step = (size_t)8 * args.hidden;
+            for (int item = cg; item < n_items; item += 4) {
+                const int m = item >= nb ? 1 : 0, ch = item - m * nb;
+                uint32_t r[16];
+                tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
+                float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(ch * 16) * args.hidden + hq * kFc1N +
+                             m * 128 + q * 32 + lane;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t r[16];
-                    tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
-                    stage_write(stg, lane, r);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (row0 + sub_row + 8 * i < N)
-                            __stcg(reinterpret_cast<float4 *>(dst + i * row_step + ch * 16), stage_read(stg, lane, i));
-                    __syncwarp();
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (ch * 16 + j < N) __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
             }
             tc_fence_before();
             __syncwarp();
@@ -378,50 +383,46 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         epi_bar_sync();
         {   // ---- y1 = relu(sum_z partial + b1) in bf16: this CTA's slice of the N x hidden outputs, float4 at a time.
-            // Four threads per output vector, each with its <= 10 partial loads in flight at once (one L2 round trip),
-            // then a fixed-order combine ((s0 + s1) + (s2 + s3)): deterministic, no atomics on data.
+            // Three threads per output vector (lanes 30 and 31 of a warp idle), each with its <= 14 partial loads in
+            // flight at once (one L2 round trip), then a fixed-order combine (s0 + s1) + s2: deterministic, no atomics
+            // on data, and the same association whatever the person count.  160 vectors per pass: one pass up to 92
+            // persons on 148 SMs (four threads per vector needed a second, nearly empty pass above 74).
             const int vec_per_row = args.hidden >> 2;
             const int total = N * vec_per_row;
             const int per = (total + G - 1) / G;
             const int v_end = min(total, (c + 1) * per);
-            const int s_quarter = (args.splits + 3) >> 2;                  // <= 10 (splits <= 40)
-            const int part = tid_e & 3;
-            const int s_lo = part * s_quarter, s_hi = min(args.splits, s_lo + s_quarter);
-            for (int v0 = c * per; v0 < v_end; v0 += kEpiWarps * 8) {
-                const int v = v0 + (tid_e >> 2);
-                const bool live = v < v_end;
+            const int s_third = (args.splits + 2) / 3;                     // <= 14 (splits <= 40)
+            const int grp = lane / 3, part = lane - 3 * grp;
+            const int s_lo = part * s_third, s_hi = min(args.splits, s_lo + s_third);
+            for (int v0 = c * per; v0 < v_end; v0 += kEpiWarps * 10) {
+                const int v = v0 + ew * 10 + grp;
+                const bool live = lane < 30 && v < v_end;
                 const int row = live ? v / vec_per_row : 0, c4 = live ? v - row * vec_per_row : 0;
                 const float *src = args.partial + (size_t)s_lo * args.split_stride + (size_t)row * args.hidden + c4 * 4;
-                float4 pv[10];
+                float4 pv[14];
 #pragma unroll
-                for (int i = 0; i < 10; ++i)
+                for (int i = 0; i < 14; ++i)
                     pv[i] = (live && s_lo + i < s_hi) ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t)i * args.split_stride))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 acc = pv[0];
 #pragma unroll
-                for (int i = 1; i < 10; ++i) {
+                for (int i = 1; i < 14; ++i) {
                     if (s_lo + i < s_hi) {
                         acc.x = __fadd_rn(acc.x, pv[i].x); acc.y = __fadd_rn(acc.y, pv[i].y);
                         acc.z = __fadd_rn(acc.z, pv[i].z); acc.w = __fadd_rn(acc.w, pv[i].w);
                     }
                 }
-#pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {                          // lanes 4k..4k+3 hold the four partial sums
-                    float4 oth;
-                    oth.x = __shfl_xor_sync(0xffffffffu, acc.x, o); oth.y = __shfl_xor_sync(0xffffffffu, acc.y, o);
-                    oth.z = __shfl_xor_sync(0xffffffffu, acc.z, o); oth.w = __shfl_xor_sync(0xffffffffu, acc.w, o);
-                    // the lower lane of each pair adds (its own) + (the upper one's): a fixed association
-                    if ((part & o) == 0) {
-                        acc.x = __fadd_rn(acc.x, oth.x); acc.y = __fadd_rn(acc.y, oth.y);
-                        acc.z = __fadd_rn(acc.z, oth.z); acc.w = __fadd_rn(acc.w, oth.w);
-                    }
-                }
+                float4 s1, s2;                                              // the sums of lanes 3g + 1 and 3g + 2
+                s1.x = __shfl_down_sync(0xffffffffu, acc.x, 1); s1.y = __shfl_down_sync(0xffffffffu, acc.y, 1);
+                s1.z = __shfl_down_sync(0xffffffffu, acc.z, 1); s1.w = __shfl_down_sync(0xffffffffu, acc.w, 1);
+                s2.x = __shfl_down_sync(0xffffffffu, acc.x, 2); s2.y = __shfl_down_sync(0xffffffffu, acc.y, 2);
+                s2.z = __shfl_down_sync(0xffffffffu, acc.z, 2); s2.w = __shfl_down_sync(0xffffffffu, acc.w, 2);
                 if (live && part == 0) {
                     const float4 bb = __ldg(reinterpret_cast<const float4 *>(args.b1 + c4 * 4));
-                    acc.x = fmaxf(__fadd_rn(acc.x, bb.x), 0.0f);
-                    acc.y = fmaxf(__fadd_rn(acc.y, bb.y), 0.0f);
-                    acc.z = fmaxf(__fadd_rn(acc.z, bb.z), 0.0f);
-                    acc.w = fmaxf(__fadd_rn(acc.w, bb.w), 0.0f);
+                    acc.x = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.x, s1.x), s2.x), bb.x), 0.0f);
+                    acc.y = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.y, s1.y), s2.y), bb.y), 0.0f);
+                    acc.z = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.z, s1.z), s2.z), bb.z), 0.0f);
+                    acc.w = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.w, s1.w), s2.w), bb.w), 0.0f);
                     const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
                     uint2 o;
                     o.x = *reinterpret_cast<const unsigned *>(&lo);
@@ -436,93 +437,54 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             grid_arrive(args.arrivals);
         }
         // ---- fc2 epilogue: logits = x + relu(acc + b2)   (detector/prn.py:22,24)
-        // This warp: columns [cg*64, +64) of the 240-column tile as 4 chunks of 16 (the last group has 3).  Chunks go
-        // through the per-warp transpose so that the residual loads and the logit stores are 64-byte row segments.  The
-        // residual does not depend on the GEMM: it is fetched BEFORE waiting for the accumulator.
+        // Lane = output column n0 + m*128 + q*32 + lane (its bias sits in a register), columns of the item = 16 persons.
+        // In place: relu(acc + b2) goes to the warp's 16 x 32 staging box and one thread issues the TMA reduce-add into
+        // x; the last 32-lane group of a 240-column tile has 16 live columns and uses the 16-wide box.
         for (int tile = c; tile < args.tiles2; tile += G) {
             const int n0 = tile * kFc2N;
-            if (tid_e < kFc2N / 4) {
-                const int n = n0 + tid_e * 4;
-                reinterpret_cast<float4 *>(s_b2)[tid_e] =
-                    n < args.D ? __ldg(reinterpret_cast<const float4 *>(args.b2 + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float bias[2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int tc = m * 128 + q * 32 + lane;
+                bias[m] = (tc < kFc2N && n0 + tc < args.D) ? __ldg(args.b2 + n0 + tc) : 0.0f;
             }
-            if (kInPlace) {
-                epi_bar_sync();                                             // s_b2 visible
-                mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
-                tc_fence_after();
-                if (tid_e == 0) stamp(args, 9);                             // fc2 accumulators complete
-                for (int m = 0; m < nm; ++m) {
-                    const int row0 = m * 128 + q * 32;
-                    if (row0 >= N) break;                                   // warp-uniform
+            mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
+            tc_fence_after();
+            if (tid_e == 0) stamp(args, 9);                                 // fc2 accumulators complete
+            for (int item = cg; item < n_items; item += 4) {
+                const int m = item >= nb ? 1 : 0, ch = item - m * nb;
+                const int tc0 = m * 128 + q * 32;                           // first tile column of this warp's lanes
+                if (tc0 >= kFc2N || n0 + tc0 >= args.D) continue;           // warp-uniform
+                const bool half = tc0 + 32 > kFc2N;                         // 16 live columns
+                const float b = m ? bias[1] : bias[0];
+                uint32_t r[16];
+                tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
+                float v[16];
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        if (cg * 64 + ch * 16 >= kFc2N) break;              // warp-uniform (last column group: 3 chunks)
-                        uint32_t r[16];
-                        tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = *reinterpret_cast<const float4 *>(s_b2 + cg * 64 + ch * 16 + 4 * j);   // broadcast
-                            r[4 * j + 0] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 0]), b.x), 0.0f));
-                            r[4 * j + 1] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 1]), b.y), 0.0f));
-                            r[4 * j + 2] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 2]), b.z), 0.0f));
-                            r[4 * j + 3] = __float_as_uint(fmaxf(__fadd_rn(__uint_as_float(r[4 * j + 3]), b.w), 0.0f));
-                        }
-                        if (lane == 0) tma_store_wait_read();               // the previous chunk has left the buffer
-                        __syncwarp();
-                        stage_write(stg, lane, r);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        // rows N .. of the last 32-row box receive meaningless sums; nothing ever reads them
-                        if (lane == 0) tma_reduce_add_2d(&tmap_out, stg, n0 + cg * 64 + ch * 16, row0);
-                    }
-                }
-            }
-            for (int m = 0; m < nm && !kInPlace; ++m) {
-                const int row0 = m * 128 + q * 32;
-                const bool rows_live = row0 < N;                            // warp-uniform
-                const int col_base = cg * 64 + sub_col;                     // column of this lane inside the tile, chunk 0
-                const size_t off = (size_t)(row0 + sub_row) * args.D + n0 + col_base;
-                const size_t row_step = (size_t)8 * args.D;
-                float4 xr[4][4];                                            // [chunk][pass]
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    const bool col_ok = rows_live && col_base + ch * 16 < kFc2N && n0 + col_base + ch * 16 < args.D;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        xr[ch][i] = (col_ok && row0 + sub_row + 8 * i < N)
-                                        ? __ldcg(reinterpret_cast<const float4 *>(args.x + off + i * row_step + ch * 16))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (m == 0) {
-                    epi_bar_sync();                                         // s_b2 visible
-                    mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
-                    tc_fence_after();
-                    if (tid_e == 0) stamp(args, 9);                         // fc2 accumulators complete
-                }
-                if (!rows_live) continue;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    if (cg * 64 + ch * 16 >= kFc2N) break;                  // warp-uniform (last column group: 3 chunks)
-                    uint32_t r[16];
-                    tmem_ld16(t_lane + (uint32_t)(m * 256 + cg * 64 + ch * 16), r);
-                    stage_write(stg, lane, r);
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(__fadd_rn(__uint_as_float(r[j]), b), 0.0f);
+                if (kInPlace) {
+                    if (lane == 0) tma_store_wait_read();                   // the previous item has left the buffer
                     __syncwarp();
-                    if (n0 + col_base + ch * 16 < args.D) {
-                        const float4 b = *reinterpret_cast<const float4 *>(s_b2 + col_base + ch * 16);
+                    if (!half) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (row0 + sub_row + 8 * i < N) {
-                                const float4 a = stage_read(stg, lane, i);
-                                float4 o;
-                                o.x = __fadd_rn(xr[ch][i].x, fmaxf(__fadd_rn(a.x, b.x), 0.0f));
-                                o.y = __fadd_rn(xr[ch][i].y, fmaxf(__fadd_rn(a.y, b.y), 0.0f));
-                                o.z = __fadd_rn(xr[ch][i].z, fmaxf(__fadd_rn(a.z, b.z), 0.0f));
-                                o.w = __fadd_rn(xr[ch][i].w, fmaxf(__fadd_rn(a.w, b.w), 0.0f));
-                                __stcs(reinterpret_cast<float4 *>(args.logits + off + i * row_step + ch * 16), o);
-                            }
-                        }
+                        for (int j = 0; j < 16; ++j) stg[j * 32 + lane] = v[j];
+                    } else if (lane < 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stg[j * 16 + lane] = v[j];
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
+                    // persons N .. of the last 16-row box receive meaningless sums; nothing ever reads them (rows past
+                    // the end of the buffer and columns past D are clipped by the tensor map)
+                    if (lane == 0) tma_reduce_add_2d(half ? &tmap_out16 : &tmap_out, stg, n0 + tc0, ch * 16);
+                } else if (tc0 + lane < kFc2N && n0 + tc0 + lane < args.D) {
+                    const size_t off = (size_t)(ch * 16) * args.D + n0 + tc0 + lane;
+                    float xr[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) xr[j] = ch * 16 + j < N ? __ldcg(args.x + off + (size_t)j * args.D) : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (ch * 16 + j < N) __stcs(args.logits + off + (size_t)j * args.D, __fadd_rn(xr[j], v[j]));
                 }
             }
             tc_fence_before();
@@ -530,7 +492,6 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
             ++round;
             if (tid_e == 0) stamp(args, 15);                                // warp 2 finished the fc2 epilogue
-            epi_bar_sync();                                                 // s_b2 may be overwritten by the next tile
         }
         if (kInPlace && lane == 0) tma_store_wait_all();                    // this thread's reduce-adds have completed
         if (tid_e == 0) stamp(args, 10);                                    // logits stored
@@ -660,13 +621,15 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
     const bool in_place = x_f32 == logits;
     if (in_place && st->out_ptr != logits) {
         const uint64_t rows = n_dev ? (uint64_t)h->prn_ws.n_max : (uint64_t)n_host;    // mpn_prn: the caller's buffer has n_host rows
-        if (!encode_2d_f32_chunk(&st->maps.out, logits, rows, (uint64_t)h->D, 32)) return -(int)cudaErrorInvalidValue;
+        if (!encode_2d_f32_box(&st->maps.out, logits, rows, (uint64_t)h->D, 32, kXBox) ||
+            !encode_2d_f32_box(&st->maps.out16, logits, rows, (uint64_t)h->D, 16, kXBox))
+            return -(int)cudaErrorInvalidValue;
         st->out_ptr = n_dev ? logits : nullptr;        // a caller's buffer may change size between calls: never cached
     }
     cudaError_t e = in_place ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true>, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2,
-                                                  st->maps.out, a)
+                                                  st->maps.out, st->maps.out16, a)
                              : cudaLaunchKernelEx(&cfg, prn_fused_kernel<false>, st->maps.x, st->maps.w1, st->maps.y1,
-                                                  st->maps.w2, st->maps.out, a);
+                                                  st->maps.w2, st->maps.out, st->maps.out16, a);
     if (e != cudaSuccess) return -(int)e;
     return 1;
 }

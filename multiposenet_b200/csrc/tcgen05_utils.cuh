@@ -187,6 +187,22 @@ inline bool encode_2d_f32_chunk(CUtensorMap *map, const void *base, uint64_t row
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 row-major [rows, cols] matrix, box = box_rows x box_cols, no swizzle: the shared-memory box is the dense
+// row-major [box_rows][box_cols] array (box_cols * 4 bytes a multiple of 16) -- TMA reduce-add stores of the fused PRN
+inline bool encode_2d_f32_box(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                              uint32_t box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 4};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, elem,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // one thread: global[box at (c0, c1)] += shared box (fp32 add performed in L2), as one bulk-async group
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *tmap, const void *smem_src, int c0, int c1)
 {
