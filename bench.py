@@ -378,22 +378,29 @@ def main():
         return bufs
 
     host_loop(Wm, 0, HOST_DEPTH)
-    barrier()
-    t0 = time.time()
-    w0 = time.perf_counter()
-    hout = host_loop(K, Wm, HOST_DEPTH)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    t1 = time.time()
-    if sampler:
-        sampler.mark(t0, t1)
+    # Two passes of K steps each, the faster one is reported (both are in the line): the pinned copies share the host's
+    # memory system with whatever else runs on the machine, and one disturbed pass has been seen to cost 60 %.
+    e2e_passes = []
+    for _ in range(2):
+        barrier()
+        t0 = time.time()
+        w0 = time.perf_counter()
+        hout = host_loop(K, Wm, HOST_DEPTH)
+        torch.cuda.synchronize()
+        pass_s = time.perf_counter() - w0
+        t1 = time.time()
+        if sampler:
+            sampler.mark(t0, t1)
+        if world > 1:
+            t = torch.tensor([pass_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pass_s = float(t.item())
+        e2e_passes.append(pass_s)
+    e2e_s = min(e2e_passes)
+    del hout
     w0 = time.perf_counter()
     host_loop(min(K, 50), 0, 1)                        # one call at a time: the latency of a single step
     serial_ms = 1e3 * (time.perf_counter() - w0) / min(K, 50)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
     h2d, d2h = det.host_traffic()
     in_bytes = set_bytes(ring[0])
 
@@ -491,7 +498,8 @@ def main():
         "dtype": "f32 (decode/NMS/crop/softmax) + " + ("bf16 tcgen05, f32 accumulate (PRN)" if args.prn_mode == "bf16" else "f32 (PRN)"),
         "data": "synthetic", "config": config_dict(wl, args, n_sets),
         "e2e": {"value": images / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / K, "in_flight": HOST_DEPTH, "serial_ms_per_step": serial_ms,
+                "ms_per_step": 1e3 * e2e_s / K, "passes_ms_per_step": [round(1e3 * x / K, 5) for x in e2e_passes],
+                "in_flight": HOST_DEPTH, "serial_ms_per_step": serial_ms,
                 "input_bytes_per_step": in_bytes,
                 "note": "class logits and heatmap logits are copied by DMA; the box codes stay in pinned host memory "
                         "and only the rows of confident anchors are gathered over PCIe by the NMS kernel"},

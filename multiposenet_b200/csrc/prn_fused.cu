@@ -363,12 +363,14 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int m = item >= nb ? 1 : 0, ch = item - m * nb;
                 uint32_t r[16];
                 tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
+                if (tid_e == 0 && item == cg) stamp(args, 11);              // warp 2: first accumulator item in registers
                 float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(ch * 16) * args.hidden + hq * kFc1N +
                              m * 128 + q * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (ch * 16 + j < N) __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
             }
+            if (tid_e == 0) stamp(args, 12);                                // warp 2: its partial sums issued
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
