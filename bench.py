@@ -38,7 +38,20 @@ if int(os.environ.get("RANK", "0")) == 0:
         os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     except AttributeError:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-os.environ["NCCL_DEBUG"] = os.environ.get("MPN_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
+# ONE JSON line on stdout: NCCL prints its version banner to stdout whenever NCCL_DEBUG is set (VERSION, WARN and INFO all
+# do), and any native library may print.  So NCCL_DEBUG is dropped unless asked for, and file descriptor 1 is pointed at
+# stderr for the life of the process; emit() writes the result line to the real stdout.
+if "MPN_NCCL_DEBUG" in os.environ:
+    os.environ["NCCL_DEBUG"] = os.environ["MPN_NCCL_DEBUG"]
+else:
+    os.environ.pop("NCCL_DEBUG", None)
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import numpy as np  # noqa: E402
 
@@ -223,7 +236,7 @@ def reference_arm(args, wl, rank, world):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(wl, args, ring_sets):
@@ -506,7 +519,7 @@ def main():
         "gpu_launches": n_launches,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
