@@ -29,7 +29,7 @@
 // cluster barrier, then CTA 0 merges and stores.  Two kernels share this arithmetic: keypoint_decode_kernel, one cluster
 // per person with the logits loaded straight into registers (lowest latency, few persons), and
 // keypoint_decode_stream_kernel, PERSISTENT clusters that walk the persons with every CTA's slab arriving by one bulk
-// copy (TMA) into a two-slot shared-memory ring, three CTAs per SM, so that the next person's bytes are in flight while
+// copy (TMA) into a two-slot shared-memory ring, two CTAs per SM, so that the next person's bytes are in flight while
 // the current one is reduced (many persons: HBM bound).
 #include <cstdlib>
 
@@ -45,7 +45,7 @@ constexpr int kLanes = 32;
 constexpr int kThreads = kNK * kLanes;   // 544
 constexpr int kCluster = 4;
 constexpr int kMaxPerThread = 16;        // positions per thread: ceil(2048 / 4 / 32)
-constexpr int kSlots = 2;                // slabs per CTA of the streaming kernel (three CTAs per SM: six slabs per SM)
+constexpr int kSlots = 2;                // slabs per CTA of the streaming kernel (two CTAs per SM: four slabs per SM)
 constexpr int kStreamSlabBytes = kSlots * (kMaxPerThread * kLanes) * kNK * 4;   // upper bound: slabs of 512 positions
 constexpr int kNone = 0x7fffffff;
 
@@ -84,8 +84,10 @@ __device__ __forceinline__ T *peer_shared(T *p, unsigned rank)
 }
 
 // Partials of the four CTAs of a cluster, held by CTA 0 (double buffered for the persistent kernel).
-// Shared memory is what limits the streaming kernel to three CTAs per SM (2 x 34272 bytes of slabs each), so the
-// scratch is packed: 76800 bytes per CTA are available, the slabs take 68544.
+// Residency: cudaOccupancyMaxActiveClusters reports 71 clusters = 2 CTAs per SM whatever the ring size (shared memory
+// and the 40-register cap would allow three: 3 x 76 KB, 3 x 21760 registers -- but 51 warps of 1280 registers do not
+// split over the four 16 K-register files of an SM).  A three-slot ring at that residency was measured: no change (the
+// inner loop is bound by instruction issue), so the ring stays at two slots and the scratch stays packed.
 struct ClusterStats {
     float m[2][kCluster][kNK];
     float s[2][kCluster][kNK];
