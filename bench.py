@@ -39,19 +39,31 @@ if int(os.environ.get("RANK", "0")) == 0:
     except AttributeError:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 # ONE JSON line on stdout: NCCL prints its version banner to stdout whenever NCCL_DEBUG is set (VERSION, WARN and INFO all
-# do), and any native library may print.  So NCCL_DEBUG is dropped unless asked for, and file descriptor 1 is pointed at
-# stderr for the life of the process; emit() writes the result line to the real stdout.
+# do), and any native library may print.  So NCCL_DEBUG is dropped unless asked for, and main() points file descriptor 1
+# at stderr for the life of the process; emit() writes the result line to the real stdout.
 if "MPN_NCCL_DEBUG" in os.environ:
     os.environ["NCCL_DEBUG"] = os.environ["MPN_NCCL_DEBUG"]
 else:
     os.environ.pop("NCCL_DEBUG", None)
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Called by main() only (importing this module must not touch the importer's descriptors)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
     sys.stdout.flush()
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -251,6 +263,7 @@ def config_dict(wl, args, ring_sets):
 # ------------------------------------------------------------------------------------------------- GPU legs
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

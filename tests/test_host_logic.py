@@ -141,3 +141,34 @@ def test_bench_and_tools_compile_and_bench_formulas_hold():
     assert bench.algorithmic_bytes("prn_fused", wl, 32, 2805, 66877, "bf16") is None      # idle above 256 persons
     assert bench.algorithmic_bytes("heatmap", wl, 8, 77, 1825, "bf16") == 2 * 72 * 160 * 160 * 8
     assert bench.algorithmic_bytes("keypoint_decode", wl, 8, 77, 1825, "bf16") == 77 * D * 4
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_prints_exactly_one_json_line_on_stdout():
+    """`bench.py --impl reference` (the CPU arm: oracle port on the host cores, no GPU involved): stdout carries ONE line,
+    it parses, and it has the keys of the bench contract; whatever else the process prints goes to stderr."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("BASELINE configs[1]")
+
+
+def test_lanes_argument_is_checked_before_anything_touches_a_device():
+    from multiposenet_b200 import DetectorLanes
+    with pytest.raises(ValueError):
+        DetectorLanes(None, lanes=0)
+
+
+def test_importing_bench_leaves_stdout_alone():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench._REAL_STDOUT is None
