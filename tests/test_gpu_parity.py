@@ -148,6 +148,19 @@ def test_detect_edge_cases(det6):
     tie["class_logits"][:, [50, 20, 900, 901]] = 1.25
     tie["encoded_boxes"] = np.zeros_like(inp["encoded_boxes"])
     _detect_case(det6, wl, tie, 0.3, 0.6, 25)
+    # degenerate boxes: th = tw = -1000 collapses a box to its centre (exp -> +0), a huge ty pushes one outside the image
+    # where the clip flattens it; TensorFlow's rule is that a zero-area box neither suppresses nor is suppressed, so the six
+    # coincident points of one location are all kept next to the ordinary box that contains them
+    flat = dict(inp, class_logits=np.full((2, A), -9.0, np.float32), encoded_boxes=np.zeros_like(inp["encoded_boxes"]))
+    flat["class_logits"][:, 600:606] = np.linspace(2.0, 1.0, 6, dtype=np.float32)       # one location, all six shapes
+    flat["encoded_boxes"][:, 600:606, 2:] = -1000.0
+    flat["class_logits"][:, 612] = 0.5                                                   # the neighbouring location, intact
+    flat["class_logits"][:, 30] = 3.0
+    flat["encoded_boxes"][:, 30, 0] = 500.0                                              # far below the image: clipped flat
+    got, want = _detect_case(det6, wl, flat, 0.3, 0.01, 25)
+    assert (want["num_boxes"] == 8).all()
+    pts = got["boxes"][0, 1:7]
+    assert (pts[:, 0] == pts[:, 2]).all() and (pts[:, 1] == pts[:, 3]).all()
 
 
 def test_detect_nchw_levels_equal_concatenated_layout(det6):
