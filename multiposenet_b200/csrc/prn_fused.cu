@@ -241,9 +241,9 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // Measured and not kept (profiles/r01f_summary.md): TMA L2 prefetches of the rest of the W2 tile issued here
             // or after barrier 1, a sliding L2 prefetch window ahead of the ring in both layers, an L2 prefetch of W1
             // from a kernel in the front half of the call, and a per-CTA rotation of the k order.  With W2 L2-resident
-            // phase 3 got only 1.1 us shorter: both streaming phases move ~97 MB (70 MB of weights + the activation
-            // boxes every CTA re-reads) from L2 to the SMs, which is ~8 us at the ~12 TB/s the L2 can deliver --
-            // they are bound by L2 -> SM bandwidth as much as by HBM.
+            // phase 3 got only 1.1 us shorter, so HBM alone is not what bounds the streaming phases; neither are the
+            // activation boxes every CTA re-reads (multicasting them inside CTA pairs: no gain), nor the ring depth, nor
+            // the number of W2 boxes on the SM before barrier 2 (profiles/r01g_*.txt).
             const int first2 = it;
             int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
             bool y1_ready = false;
