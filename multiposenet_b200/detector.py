@@ -69,6 +69,30 @@ def _ptr(t):
     return C.c_void_p(t.ctypes.data)
 
 
+def post_filter(raw, score_threshold):
+    """The host-side tail of the reference's Detector.__call__ (inference/detector.py:49-59) on a dict of numpy outputs
+    (the seven named tensors + person_offsets): keypoint rows cut to the person count; for ONE image the batch dimension
+    is stripped from everything except keypoint_scores / keypoint_positions (:49-52) and the rows with
+    `score > score_threshold` are kept (:54-59, strict; `num_boxes` stays unfiltered).  For B > 1 the padded per-image
+    tensors of create_pb.py:53-61 are returned with `person_offsets`."""
+    raw = dict(raw)
+    B = raw["num_boxes"].shape[0]
+    N = int(raw["person_offsets"][-1])
+    raw["keypoint_scores"] = raw["keypoint_scores"][:N]
+    raw["keypoint_positions"] = raw["keypoint_positions"][:N]
+    if B > 1:
+        return raw
+    out = {k: (v if k in ("keypoint_scores", "keypoint_positions", "person_offsets") else v[0]) for k, v in raw.items()}
+    out.pop("person_offsets")
+    n = int(out["num_boxes"])
+    to_keep = out["scores"][:n] > score_threshold
+    out["boxes"] = out["boxes"][:n][to_keep]
+    out["scores"] = out["scores"][:n][to_keep]
+    out["keypoint_positions"] = out["keypoint_positions"][to_keep]
+    out["keypoint_scores"] = out["keypoint_scores"][to_keep]
+    return out
+
+
 class Detector:
     """B200 replacement of the post-network part of the reference's frozen graph."""
 
@@ -331,22 +355,7 @@ class Detector:
             self.synchronize()
             raw = {k: (v.numpy().copy() if copy else v.numpy()) for k, v in bufs.items()
                    if return_heatmaps or k not in ("keypoint_heatmaps", "segmentation_masks")}
-        B = raw["num_boxes"].shape[0]
-        N = int(raw["person_offsets"][-1])
-        raw["keypoint_scores"] = raw["keypoint_scores"][:N]
-        raw["keypoint_positions"] = raw["keypoint_positions"][:N]
-        if B > 1:
-            return raw
-        # inference/detector.py:49-59: strip the batch dimension, keep rows with score > score_threshold
-        out = {k: (v if k in ("keypoint_scores", "keypoint_positions", "person_offsets") else v[0]) for k, v in raw.items()}
-        out.pop("person_offsets")
-        n = int(out["num_boxes"])
-        to_keep = out["scores"][:n] > score_threshold
-        out["boxes"] = out["boxes"][:n][to_keep]
-        out["scores"] = out["scores"][:n][to_keep]
-        out["keypoint_positions"] = out["keypoint_positions"][to_keep]
-        out["keypoint_scores"] = out["keypoint_scores"][to_keep]
-        return out
+        return post_filter(raw, score_threshold)
 
     # ------------------------------------------------------------------ single stages (CUDA tensors)
     def anchors(self, height, width):
