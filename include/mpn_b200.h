@@ -174,6 +174,16 @@ MPN_API int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p,
 MPN_API int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
                  float *keypoint_heatmaps, float *segmentation_masks, float *minmax, void *stream);
 
+/* The same stage in the two-pass form mpn_run uses whenever the crops are taken from the padded normalised map (every
+ * BASELINE configuration except 1024 x 1024 x 64): create_pb.py:73-76 AND :90-94.  Pass 1 takes min / max of the LOGITS
+ * (the sigmoid recipe is monotone over all floats -- verified exhaustively -- so the extreme activations are the
+ * activations of the extreme logits, bit for bit); pass 2 writes keypoint_heatmaps, segmentation_masks and the normalised,
+ * masked map `normalised` [B, hh, ww, 20]: channels 0..16 = (kh - m) / (M - m) * float(M > 0.2), channels 17..19 are
+ * padding and are NOT written (NULL: the map stays in the handle's workspace).  minmax as in mpn_heatmaps.            */
+MPN_API int mpn_heatmaps_normalised(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height,
+                                    int32_t hm_width, float *keypoint_heatmaps, float *segmentation_masks, float *minmax,
+                                    float *normalised, void *stream);
+
 /* SURVEY.md section 8(f) row 2, the step in front of the path: the tail of KeypointSubnet fused with mpn_heatmaps --
  * detector/keypoint_subnet.py:49-58 (heatmaps = conv2d(x, 18, kernel_size=1) + bias, then NCHW -> NHWC) followed by
  * create_pb.py:73-76,90,92.  features [B, 64, hh, ww] f32 NCHW (x after final_bn + ReLU), weight [64, 18] f32 (the
@@ -187,6 +197,13 @@ MPN_API int mpn_heatmap_head(mpn_handle *h, const float *features, const float *
  * minmax [B,K,2] or NULL (no normalisation) -> crops [N, crop_h, crop_w, K] f32                        */
 MPN_API int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax, int32_t batch, int32_t hm_height,
              int32_t hm_width, const float *boxes, const int32_t *box_ind, int32_t n, float *crops, void *stream);
+
+/* tf.image.crop_and_resize create_pb.py:106-109 of an already normalised map in the padded layout of
+ * mpn_heatmaps_normalised ([B, hh, ww, 20]; the crop kernel of mpn_run wherever that map exists): crops_f32 [N, crop_h,
+ * crop_w, K] f32 and / or crops_bf16 (the same values rounded to nearest even, bfloat16 bits) -- either may be NULL.   */
+MPN_API int mpn_crop_padded(mpn_handle *h, const float *normalised, int32_t batch, int32_t hm_height, int32_t hm_width,
+                            const float *boxes, const int32_t *box_ind, int32_t n, float *crops_f32, uint16_t *crops_bf16,
+                            void *stream);
 
 /* detector/prn.py:5-25: crops [N, D] f32 -> logits [N, D] f32.  logits == crops (bf16 mode only) computes in place:
  * x += relu(fc2(relu(fc1(x)))), which is how mpn_run uses it (the residual addition then happens in L2 by a TMA
@@ -205,6 +222,21 @@ MPN_API int mpn_get_keypoints(mpn_handle *h, const float *heatmaps, int32_t hh, 
 /* Element-wise device exp / sigmoid of the path (bit-level test hooks): y[i] = f(x[i]) */
 MPN_API int mpn_test_exp(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
 MPN_API int mpn_test_sigmoid(mpn_handle *h, const float *x, float *y, int64_t n, void *stream);
+
+/* Bit-level test hook: walks `count` consecutive floats in increasing order starting at ordered key `key_begin` (key k <
+ * 2^31 is the negative float with bits ~k, k >= 2^31 the positive float with bits k - 2^31) and adds to *violations (a
+ * DEVICE counter the caller zeroes) the number of neighbours x < x' with sigmoid(x) > sigmoid(x').  Zero over the whole
+ * range is what lets mpn_run take min / max of the logits instead of the activations.                        */
+MPN_API int mpn_test_sigmoid_monotone(mpn_handle *h, uint32_t key_begin, uint64_t count, uint64_t *violations, void *stream);
+
+/* Test hook: copies one internal buffer of the most recent mpn_run to `dst` (host or device memory; waits for the device).
+ * NORMALISED [B, hh, ww, 20] f32 (padded crop path only), CROPS_F32 [n_max, D] f32 and CROPS_BF16 [n_max, D] bfloat16 (the
+ * PRN inputs; in bf16 mode the PRN runs in place, so fetch them from a run with the PRN skipped: mpn_debug_skip(16 | 32)),
+ * LOGITS [n_max, D] f32 (what the keypoint decode read), MINMAX [B, K, 2], PERSON_BOX [n_max, 4], PERSON_IMAGE [n_max];
+ * rows >= person_offsets[B] are stale.  dst == NULL only reports the size in *bytes_out.                       */
+enum { MPN_DEBUG_NORMALISED = 0, MPN_DEBUG_CROPS_F32 = 1, MPN_DEBUG_CROPS_BF16 = 2, MPN_DEBUG_LOGITS = 3, MPN_DEBUG_MINMAX = 4,
+       MPN_DEBUG_PERSON_BOX = 5, MPN_DEBUG_PERSON_IMAGE = 6 };
+MPN_API int mpn_debug_fetch(mpn_handle *h, int32_t what, void *dst, int64_t capacity_bytes, int64_t *bytes_out);
 
 /* Per-kernel device times of the most recent mpn_run (CUDA events recorded on the run's stream between the kernels;
  * used by bench.py for the roofline figures -- leave it off in production, every event costs a little launch time).

@@ -22,6 +22,8 @@ MPN_ERR_CAPACITY = -5
 PRN_FP32 = 0
 PRN_BF16 = 1
 HOST_DEPTH = 3          # MPN_HOST_DEPTH
+DEBUG_BUFFERS = {"normalised": 0, "crops_f32": 1, "crops_bf16": 2, "logits": 3, "minmax": 4, "person_box": 5,
+                 "person_image": 6}          # MPN_DEBUG_*
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -77,6 +79,10 @@ SYMBOLS = {
                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_heatmaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
+    "mpn_heatmaps_normalised": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpn_crop_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_heatmap_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpn_crop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -87,6 +93,8 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p]),
     "mpn_test_exp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mpn_test_sigmoid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mpn_test_sigmoid_monotone": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mpn_debug_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "mpn_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "mpn_get_profile": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "mpn_debug_fused_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),

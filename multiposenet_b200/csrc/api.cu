@@ -338,9 +338,11 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     MPN_ALLOC(h->kh_ws, B * h->max_hm_pix * 17);
     MPN_ALLOC(h->nh_ws, B * h->max_hm_pix * 20);   // padded pixels (heatmap.cu: kPadCh)
     MPN_ALLOC(h->minmax_ws, B * 17 * 2);
-    MPN_ALLOC(h->hm_partial, B * (size_t)((h->max_hm_pix / 64 + 1) / 2 + 1) * 17 * 2);
+    h->hm_partial_chunks = (h->max_hm_pix / 64 + 1) / 2 + 1;      // per image; every heatmap launcher stays within it
+    MPN_ALLOC(h->hm_partial, B * (size_t)h->hm_partial_chunks * 17 * 2);
     MPN_ALLOC(h->hm_counter, B);
     cudaMemset(h->hm_counter, 0, B * sizeof(unsigned int));
+    cudaMemset(h->nh_ws, 0, B * h->max_hm_pix * 20 * sizeof(float));     // pad channels 17..19 stay zero for good
     MPN_ALLOC(h->crops_f32, NPpad * D);
     MPN_ALLOC(h->logits, NPpad * D);
     MPN_ALLOC(h->b1, Hd);
@@ -348,7 +350,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     if (cfg->prn_modes & 1) {
         MPN_ALLOC(h->W1, D * Hd);
         MPN_ALLOC(h->W2, Hd * D);
-        h->prn_ws.partial_floats = (NP > 2400 ? NP : 2400) * Hd;
+        h->prn_ws.partial_floats = (NPpad > 2400 ? NPpad : 2400) * Hd;     // mpn_prn accepts up to NPpad rows
         MPN_ALLOC(h->prn_ws.partial, h->prn_ws.partial_floats);
         MPN_ALLOC(h->prn_ws.y1, NPpad * Hd);
     }
@@ -385,15 +387,29 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
         mpn_destroy(h);
         return MPN_ERR_CUDA;
     }
+    if (heatmap_prepare(&h->waves) != 0) {
+        fail(nullptr, MPN_ERR_CUDA, "heatmap kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mpn_destroy(h);
+        return MPN_ERR_CUDA;
+    }
     if (detect_prepare() != 0) {
         fail(nullptr, MPN_ERR_CUDA, "sort/NMS kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         mpn_destroy(h);
         return MPN_ERR_CUDA;
     }
-    if (kpdecode_prepare(h->own_stream) != 0 || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
-        fail(nullptr, MPN_ERR_CUDA, "keypoint decode setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-        mpn_destroy(h);
-        return MPN_ERR_CUDA;
+    {
+        const int rk = kpdecode_prepare(h->own_stream, cfg->crop_height, cfg->crop_width, &h->decode_clusters);
+        if (rk == -2) {
+            fail(nullptr, MPN_ERR_UNSUPPORTED, "crop size %dx%d is not covered by the keypoint decode kernel", cfg->crop_height,
+                 cfg->crop_width);
+            mpn_destroy(h);
+            return MPN_ERR_UNSUPPORTED;
+        }
+        if (rk != 0 || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
+            fail(nullptr, MPN_ERR_CUDA, "keypoint decode setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+            mpn_destroy(h);
+            return MPN_ERR_CUDA;
+        }
     }
     if (cfg->prn_modes & 2) {
         int rc = prn_bf16_prepare(h);
@@ -423,10 +439,10 @@ void mpn_destroy(mpn_handle *h)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (HostSlot &sl : h->slots) {
-        void *sp[] = {sl.cls, sl.enc, sl.hml, sl.kh, sl.seg, sl.boxes, sl.scores, sl.kscores, sl.kpos, sl.num, sl.offsets,
-                      (void *)sl.enc_word};
+        void *sp[] = {sl.cls, sl.enc, sl.hml, sl.kh, sl.seg, sl.small_dev, (void *)sl.enc_word};
         for (void *p : sp)
             if (p) cudaFree(p);
+        if (sl.small_host) cudaFreeHost(sl.small_host);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
         if (sl.ev_out) cudaEventDestroy(sl.ev_out);
@@ -510,10 +526,52 @@ int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int3
     if (batch < 1 || batch > h->cfg.max_batch) return fail(h, MPN_ERR_CAPACITY, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
     if (hm_height < 1 || hm_width < 1 || (hm_height * hm_width) % 64 != 0)
         return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 64 (it is for images divisible by 128)");
+    if ((long long)hm_height * hm_width > h->max_hm_pix)     // the per-CTA min / max array is sized for the handle's capacity
+        return fail(h, MPN_ERR_CAPACITY, "heatmap %dx%d exceeds the handle's capacity of %d pixels", hm_height, hm_width, h->max_hm_pix);
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     return launched(h, launch_heatmaps(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
-                                       h->minmax_ws, minmax, h->hm_partial, h->hm_counter, (cudaStream_t)stream), true,
-                    "heatmaps");
+                                       h->minmax_ws, minmax, h->hm_partial, h->hm_counter, h->waves.one_pass, (cudaStream_t)stream),
+                    true, "heatmaps");
+}
+
+int mpn_heatmaps_normalised(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
+                            float *keypoint_heatmaps, float *segmentation_masks, float *minmax, float *normalised, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!heatmap_logits || !keypoint_heatmaps) return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap pointer is NULL");
+    if (batch < 1 || batch > h->cfg.max_batch) return fail(h, MPN_ERR_CAPACITY, "batch %d outside [1, %d]", batch, h->cfg.max_batch);
+    if (hm_height < 1 || hm_width < 1 || (hm_height * hm_width) % 64 != 0)
+        return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 64 (it is for images divisible by 128)");
+    if ((long long)hm_height * hm_width > h->max_hm_pix)
+        return fail(h, MPN_ERR_CAPACITY, "heatmap %dx%d exceeds the handle's capacity of %d pixels", hm_height, hm_width, h->max_hm_pix);
+    if (reinterpret_cast<uintptr_t>(heatmap_logits) % 16 != 0 || (normalised && reinterpret_cast<uintptr_t>(normalised) % 16 != 0))
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits / normalised must be 16-byte aligned");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launched(h, launch_logit_minmax(heatmap_logits, batch, hm_height, hm_width, h->minmax_ws, h->hm_partial,
+                                             h->hm_partial_chunks, h->hm_counter, h->waves.minmax, s), true, "logit min/max");
+    if (rc) return rc;
+    return launched(h, launch_heatmap_norm(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
+                                           h->minmax_ws, normalised ? normalised : h->nh_ws, minmax, h->waves.norm, s), false,
+                    "heatmaps + normalise");
+}
+
+int mpn_crop_padded(mpn_handle *h, const float *normalised, int32_t batch, int32_t hm_height, int32_t hm_width,
+                    const float *boxes, const int32_t *box_ind, int32_t n, float *crops_f32, uint16_t *crops_bf16, void *stream)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!normalised || !boxes || !box_ind || (!crops_f32 && !crops_bf16)) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
+    if (n < 0 || batch < 1 || hm_height < 1 || hm_width < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (reinterpret_cast<uintptr_t>(normalised) % 16 != 0 || reinterpret_cast<uintptr_t>(boxes) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(crops_f32) % 16 != 0 || reinterpret_cast<uintptr_t>(crops_bf16) % 8 != 0)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "normalised / boxes / crops must be 16-byte aligned");
+    if (!crop_padded_supported(h->cfg.crop_height, h->cfg.crop_width))
+        return fail(h, MPN_ERR_UNSUPPORTED, "the padded crop kernel does not cover this crop size");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (n == 0) { h->last_launches = 0; return MPN_OK; }
+    return launched(h, launch_crop_padded(normalised, hm_height, hm_width, boxes, box_ind, nullptr, n, n, h->cfg.crop_height,
+                                          h->cfg.crop_width, crops_f32, reinterpret_cast<__nv_bfloat16 *>(crops_bf16),
+                                          (cudaStream_t)stream), true, "crop (padded)");
 }
 
 int mpn_heatmap_head(mpn_handle *h, const float *features, const float *weight, const float *bias, int32_t batch,
@@ -572,8 +630,8 @@ int mpn_keypoint_decode(mpn_handle *h, const float *logits, int32_t n, float *sc
     if (!logits || !scores || !positions) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
     if (n < 0) return fail(h, MPN_ERR_INVALID_ARGUMENT, "n is negative");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
-    return launched(h, launch_keypoint_decode(logits, nullptr, n, n, h->cfg.crop_height, h->cfg.crop_width, scores,
-                                              positions, argmax, (cudaStream_t)stream), true, "keypoint decode");
+    return launched(h, launch_keypoint_decode(logits, nullptr, n, n, h->cfg.crop_height, h->cfg.crop_width,
+                                              h->decode_clusters, scores, positions, argmax, (cudaStream_t)stream), true, "keypoint decode");
 }
 
 int mpn_get_keypoints(mpn_handle *h, const float *heatmaps, int32_t hh, int32_t ww, const double box[4],
@@ -621,37 +679,44 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     }
     const unsigned skip = h->debug_skip;
     int rc = MPN_OK;
-    // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
-    // The heatmap grid (thousands of CTAs) is released only once the candidate scan has finished, i.e. at the moment
-    // sort/NMS becomes ready as well: its 8 big CTAs (512 threads, 64 registers) are placed first on an empty GPU and the
-    // heatmap CTAs fill the other SMs.  Released together with the candidate scan they would occupy every SM for their
-    // whole 2.7 waves and sort/NMS would start only when they drain (measured: no overlap at all).
-    if (!(skip & 1u))
-        rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, sd, true,
-                       fork ? h->ev_cand : nullptr);
-    if (rc) return rc;
-    if (fork) {
-        MPN_CUDA(h, cudaEventRecord(h->ev_join, sd));
-        if (!(skip & 1u)) MPN_CUDA(h, cudaStreamWaitEvent(sa, h->ev_cand, 0));
-    }
-    // 2. heatmap sigmoid / split / min-max, then normalise the whole map once   (create_pb.py:73-76, 90-94)
-    const int hh = in->height / h->cfg.downsample, ww = in->width / h->cfg.downsample;
-    float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
-    if (!(skip & 2u))
-        rc = launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks, h->minmax_ws,
-                                         nullptr, h->hm_partial, h->hm_counter, sa), false, "heatmaps");
-    if (rc) return rc;
     // Two ways to the normalised taps: normalise the WHOLE map once into a padded workspace and crop from that (one
     // division per heatmap value, 16-byte tap loads), or crop from keypoint_heatmaps and normalise every tap (4 divisions
     // per crop sample, scalar tap loads, but no pass over the map).  Large maps with few persons take the second way
     // (1024 x 1024 x 64 with <= 25 boxes per image: 667 -> 507 us per call), everything else the first (crowded 640 x 640
     // x 32: 887 against 1134 us; one 512 x 512 image: 58.3 against 62.4 us); so do crop sizes the padded kernel does
     // not cover.
-    const long long map_pixels = (long long)in->batch * (in->height / h->cfg.downsample) * (in->width / h->cfg.downsample);
+    const int hh = in->height / h->cfg.downsample, ww = in->width / h->cfg.downsample;
+    const long long map_pixels = (long long)in->batch * hh * ww;
     const bool per_tap = map_pixels > 1500LL * in->batch * p->max_detections;
     const bool padded = crop_padded_supported(h->cfg.crop_height, h->cfg.crop_width) && !per_tap;
-    if (!(skip & 4u) && padded)
-        rc = launched(h, launch_normalise(kh, h->minmax_ws, in->batch, hh, ww, h->nh_ws, sa), false, "normalise");
+    float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
+    // 1a. padded path, pass 1 of the heatmap stage: min / max of the logits (create_pb.py:90,92 through the monotone
+    //     sigmoid).  A short HBM stream with no dependency on anything: it runs BESIDE the candidate scan.
+    if (padded && !(skip & 2u))
+        rc = launched(h, launch_logit_minmax(in->heatmap_logits, in->batch, hh, ww, h->minmax_ws, h->hm_partial,
+                                             h->hm_partial_chunks, h->hm_counter, h->waves.minmax, sa), true, "logit min/max");
+    if (rc) return rc;
+    // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
+    // The big heatmap grid (thousands of CTAs) is released only once the candidate scan has finished, i.e. at the moment
+    // sort/NMS becomes ready as well: its few big CTAs (512 threads, 100 KB) are placed first on an empty GPU and the
+    // heatmap CTAs fill the other SMs.  Released together with the candidate scan they would occupy every SM for their
+    // whole life and sort/NMS would start only when they drain (measured: no overlap at all).
+    if (!(skip & 1u))
+        rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, sd,
+                       !(padded && !(skip & 2u)), fork ? h->ev_cand : nullptr);
+    if (rc) return rc;
+    if (fork) {
+        MPN_CUDA(h, cudaEventRecord(h->ev_join, sd));
+        if (!(skip & 1u)) MPN_CUDA(h, cudaStreamWaitEvent(sa, h->ev_cand, 0));
+    }
+    // 2. heatmap activation / split (create_pb.py:73-76) and normalisation (:90-94): pass 2 of the padded path writes
+    //    keypoint_heatmaps, segmentation_masks and the padded normalised map at once; the per-tap path needs the
+    //    activations and their min / max only (one pass).
+    if (!(skip & 2u))
+        rc = padded ? launched(h, launch_heatmap_norm(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks,
+                                                      h->minmax_ws, h->nh_ws, nullptr, h->waves.norm, sa), false, "heatmaps + normalise")
+                    : launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks,
+                                                  h->minmax_ws, nullptr, h->hm_partial, h->hm_counter, h->waves.one_pass, sa), false, "heatmaps");
     if (rc) return rc;
     if (fork) MPN_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     // 3. crop_and_resize                                     (create_pb.py:106-109)
@@ -671,12 +736,14 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     // bf16 mode: in place -- the logits overwrite the fp32 crops (the large-batch fc2 then adds the residual in L2 with a
     // TMA reduce-add instead of loading it; the single-kernel PRN loads and stores every element in the same thread)
     float *prn_out = (bf16 && (h->big || (h->fused && n_max <= kPrnFusedMaxRows))) ? h->crops_f32 : h->logits;
+    h->last_run.batch = in->batch; h->last_run.hh = hh; h->last_run.ww = ww; h->last_run.n_max = n_max;
+    h->last_run.padded = padded; h->last_run.prn_out = prn_out; h->last_run.valid = true;
     if (!(skip & 16u)) rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, prn_out, s, false);
     if (rc) return rc;
     // 5. softmax / argmax                                    (create_pb.py:115-142)
     if (skip & 32u) return MPN_OK;
     return launched(h, launch_keypoint_decode(prn_out, n_dev, 0, n_max, h->cfg.crop_height, h->cfg.crop_width,
-                                              out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
+                                              h->decode_clusters, out->keypoint_scores, out->keypoint_positions, nullptr, s), false,
                     "keypoint decode");
 }
 
@@ -771,6 +838,11 @@ int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_
     const bool flat = in->class_logits != nullptr && in->encoded_boxes != nullptr;
     const bool levels = in->level_class != nullptr && in->level_boxes != nullptr;
     if (!flat && !levels) return fail(h, MPN_ERR_INVALID_ARGUMENT, "need class_logits+encoded_boxes or level_class+level_boxes");
+    // per-call pointer preconditions are checked HERE: a graph replay never reaches the checks of the launchers
+    if (flat && reinterpret_cast<uintptr_t>(in->encoded_boxes) % 16 != 0)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "encoded_boxes must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(in->heatmap_logits) % 16 != 0)
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits must be 16-byte aligned");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
     if (h->prof.on) {              // per-kernel timing: one stream, direct launches
@@ -789,6 +861,16 @@ int mpn_run(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_
     return enqueue_path(h, in, p, out, s, s != nullptr && s != cudaStreamLegacy);
 }
 
+// Offsets of boxes, scores, keypoint_scores, keypoint_positions, num_boxes, person_offsets inside a slot's small-output
+// block for a call of B images and NP = B * max_detections person rows (16-byte aligned sub-ranges); offs[6] = total.
+static void small_layout(size_t B, size_t NP, size_t offs[7])
+{
+    const size_t bytes[6] = {NP * 16, NP * 4, NP * 68, NP * 136, B * 4, (B + 1) * 4};
+    size_t o = 0;
+    for (int i = 0; i < 6; ++i) { offs[i] = o; o += (bytes[i] + 15) / 16 * 16; }
+    offs[6] = o;
+}
+
 static int ensure_staging(mpn_handle *h)
 {
     if (h->staging_ready) return MPN_OK;
@@ -801,12 +883,11 @@ static int ensure_staging(mpn_handle *h)
         MPN_CUDA(h, dalloc(&sl.hml, B * P * 18));
         MPN_CUDA(h, dalloc(&sl.kh, B * P * 17));
         MPN_CUDA(h, dalloc(&sl.seg, B * P));
-        MPN_CUDA(h, dalloc(&sl.boxes, NP * 4));
-        MPN_CUDA(h, dalloc(&sl.scores, NP));
-        MPN_CUDA(h, dalloc(&sl.kscores, NP * 17));
-        MPN_CUDA(h, dalloc(&sl.kpos, NP * 34));
-        MPN_CUDA(h, dalloc(&sl.num, B));
-        MPN_CUDA(h, dalloc(&sl.offsets, B + 1));
+        // one block for the six small outputs (laid out per call by small_layout)
+        size_t offs[7];
+        small_layout(B, NP, offs);
+        MPN_CUDA(h, dalloc(&sl.small_dev, offs[6]));
+        MPN_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&sl.small_host), offs[6], cudaHostAllocDefault));
         MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
         MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
         MPN_CUDA(h, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
@@ -822,6 +903,19 @@ static const float *mapped_alias(const float *host)
     if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (at.type == cudaMemoryTypeHost && at.devicePointer) return static_cast<const float *>(at.devicePointer);
     return nullptr;
+}
+
+// Waits for the slot's copy-out and hands the small outputs from the pinned block to the caller's buffers (once).
+static int finish_slot(mpn_handle *h, HostSlot &sl)
+{
+    if (!sl.used) return MPN_OK;
+    MPN_CUDA(h, cudaEventSynchronize(sl.ev_out));
+    if (sl.scatter_pending) {
+        for (int i = 0; i < sl.n_scatter; ++i)
+            if (sl.scatter[i].dst && sl.scatter[i].bytes) memcpy(sl.scatter[i].dst, sl.small_host + sl.scatter[i].off, sl.scatter[i].bytes);
+        sl.scatter_pending = false;
+    }
+    return MPN_OK;
 }
 
 int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out, int64_t *ticket)
@@ -840,6 +934,8 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
     rc = ensure_staging(h);
     if (rc) return rc;
     HostSlot &sl = h->slots[h->next_ticket % kHostSlots];
+    rc = finish_slot(h, sl);           // a caller that never waited for this slot's previous ticket still gets its outputs
+    if (rc) return rc;
     const size_t B = in->batch, A = count_anchors(h->cfg, in->height, in->width);
     const size_t P = (size_t)(in->height / 4) * (in->width / 4), NP = B * p->max_detections;
     // ---- feed (inference/detector.py:47) on the copy-in stream.  The box codes are only ever gathered for the few
@@ -849,7 +945,10 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
     if (sl.used) MPN_CUDA(h, cudaStreamWaitEvent(si, sl.ev_out, 0));     // slot drained by its previous call
     MPN_CUDA(h, cudaMemcpyAsync(sl.cls, in->class_logits, B * A * 4, cudaMemcpyHostToDevice, si));
     MPN_CUDA(h, cudaMemcpyAsync(sl.hml, in->heatmap_logits, B * P * 72, cudaMemcpyHostToDevice, si));
+    // gathered in place only when the device sees the buffer AND its rows are 16-byte aligned (the kernels load a code as
+    // one float4; a graph replay does not re-run the alignment check of the capture); anything else is copied
     const float *enc = mapped_alias(in->encoded_boxes);
+    if (enc && reinterpret_cast<uintptr_t>(enc) % 16 != 0) enc = nullptr;
     h->last_h2d_bytes = (int64_t)(B * A * 4 + B * P * 72);
     if (!enc) {
         if (!sl.enc) MPN_CUDA(h, dalloc(&sl.enc, (size_t)h->cfg.max_batch * h->max_anchors * 4));
@@ -870,6 +969,15 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
     mpn_inputs din = *in;
     din.class_logits = sl.cls; din.encoded_boxes = enc; din.heatmap_logits = sl.hml;
     din.level_class = nullptr; din.level_boxes = nullptr;
+    size_t offs[7];
+    small_layout(B, NP, offs);
+    sl.small_bytes = offs[6];
+    sl.boxes = reinterpret_cast<float *>(sl.small_dev + offs[0]);
+    sl.scores = reinterpret_cast<float *>(sl.small_dev + offs[1]);
+    sl.kscores = reinterpret_cast<float *>(sl.small_dev + offs[2]);
+    sl.kpos = reinterpret_cast<float *>(sl.small_dev + offs[3]);
+    sl.num = reinterpret_cast<int *>(sl.small_dev + offs[4]);
+    sl.offsets = reinterpret_cast<int *>(sl.small_dev + offs[5]);
     mpn_outputs dout;
     dout.boxes = sl.boxes; dout.scores = sl.scores; dout.num_boxes = sl.num;
     dout.keypoint_heatmaps = sl.kh; dout.segmentation_masks = out->segmentation_masks ? sl.seg : nullptr;
@@ -881,15 +989,23 @@ int mpn_submit_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, co
     MPN_CUDA(h, cudaEventRecord(sl.ev_comp, sc));
     // ---- fetch (inference/detector.py:48) on the copy-out stream
     MPN_CUDA(h, cudaStreamWaitEvent(so, sl.ev_comp, 0));
-    MPN_CUDA(h, cudaMemcpyAsync(out->boxes, sl.boxes, NP * 16, cudaMemcpyDeviceToHost, so));
-    MPN_CUDA(h, cudaMemcpyAsync(out->scores, sl.scores, NP * 4, cudaMemcpyDeviceToHost, so));
-    MPN_CUDA(h, cudaMemcpyAsync(out->num_boxes, sl.num, B * 4, cudaMemcpyDeviceToHost, so));
-    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_scores, sl.kscores, NP * 17 * 4, cudaMemcpyDeviceToHost, so));
-    MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_positions, sl.kpos, NP * 34 * 4, cudaMemcpyDeviceToHost, so));
-    h->last_d2h_bytes = (int64_t)(NP * (16 + 4 + 68 + 136) + B * 4);
-    if (out->person_offsets) {
-        MPN_CUDA(h, cudaMemcpyAsync(out->person_offsets, sl.offsets, (B + 1) * 4, cudaMemcpyDeviceToHost, so));
-        h->last_d2h_bytes += (int64_t)((B + 1) * 4);
+    MPN_CUDA(h, cudaMemcpyAsync(sl.small_host, sl.small_dev, sl.small_bytes, cudaMemcpyDeviceToHost, so));
+    h->last_d2h_bytes = (int64_t)sl.small_bytes;
+    {
+        const unsigned char *base = sl.small_dev;
+        auto rec = [&](int i, void *dst, const void *dev, size_t bytes) {
+            sl.scatter[i].dst = dst;
+            sl.scatter[i].off = (size_t)(static_cast<const unsigned char *>(dev) - base);
+            sl.scatter[i].bytes = bytes;
+        };
+        rec(0, out->boxes, sl.boxes, NP * 16);
+        rec(1, out->scores, sl.scores, NP * 4);
+        rec(2, out->keypoint_scores, sl.kscores, NP * 68);
+        rec(3, out->keypoint_positions, sl.kpos, NP * 136);
+        rec(4, out->num_boxes, sl.num, B * 4);
+        rec(5, out->person_offsets, sl.offsets, out->person_offsets ? (B + 1) * 4 : 0);
+        sl.n_scatter = 6;
+        sl.scatter_pending = true;
     }
     if (out->keypoint_heatmaps) {
         MPN_CUDA(h, cudaMemcpyAsync(out->keypoint_heatmaps, sl.kh, B * P * 68, cudaMemcpyDeviceToHost, so));
@@ -912,8 +1028,7 @@ int mpn_wait(mpn_handle *h, int64_t ticket)
     if (ticket < 0 || ticket >= h->next_ticket) return fail(h, MPN_ERR_INVALID_ARGUMENT, "unknown ticket %lld", (long long)ticket);
     // if the slot has been re-used since, this waits for the later call, which is ordered after this one
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
-    MPN_CUDA(h, cudaEventSynchronize(h->slots[ticket % kHostSlots].ev_out));
-    return MPN_OK;
+    return finish_slot(h, h->slots[ticket % kHostSlots]);
 }
 
 int mpn_run_host(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, const mpn_outputs *out)
@@ -927,7 +1042,13 @@ int mpn_synchronize(mpn_handle *h)
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->staging_ready) MPN_CUDA(h, cudaStreamSynchronize(h->in_stream));
     MPN_CUDA(h, cudaStreamSynchronize(h->own_stream));
-    if (h->staging_ready) MPN_CUDA(h, cudaStreamSynchronize(h->out_stream));
+    if (h->staging_ready) {
+        MPN_CUDA(h, cudaStreamSynchronize(h->out_stream));
+        for (HostSlot &sl : h->slots) {
+            const int rc = finish_slot(h, sl);
+            if (rc) return rc;
+        }
+    }
     return MPN_OK;
 }
 
@@ -945,9 +1066,52 @@ int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     MPN_CUDA(h, cudaDeviceSynchronize());
     int g = 0;
+    // the trace pointer is a kernel argument baked into the captured graphs: drop them whenever tracing is switched
+    for (GraphEntry &e : h->graphs)
+        if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
+    h->graph_miss_streak = 0;
     const int rc = prn_fused_trace(h, enable, reinterpret_cast<unsigned long long *>(host_out), capacity, &g);
     if (grid_out) *grid_out = g;
     return rc == MPN_OK ? MPN_OK : fail(h, rc, "fused PRN trace unavailable");
+}
+
+int mpn_debug_fetch(mpn_handle *h, int32_t what, void *dst, int64_t capacity_bytes, int64_t *bytes_out)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    if (!h->last_run.valid) return fail(h, MPN_ERR_INVALID_ARGUMENT, "no mpn_run has been issued on this handle");
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    MPN_CUDA(h, cudaDeviceSynchronize());
+    const size_t B = h->last_run.batch, pix = (size_t)h->last_run.hh * h->last_run.ww, n = h->last_run.n_max, D = h->D;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+    case MPN_DEBUG_NORMALISED:
+        if (!h->last_run.padded) return fail(h, MPN_ERR_UNSUPPORTED, "the last run took the per-tap crop path: no normalised map");
+        src = h->nh_ws; bytes = B * pix * 20 * 4; break;
+    case MPN_DEBUG_CROPS_F32: src = h->crops_f32; bytes = n * D * 4; break;
+    case MPN_DEBUG_CROPS_BF16:
+        if (!h->crops_bf16) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
+        src = h->crops_bf16; bytes = n * D * 2; break;
+    case MPN_DEBUG_LOGITS: src = h->last_run.prn_out; bytes = n * D * 4; break;
+    case MPN_DEBUG_MINMAX: src = h->minmax_ws; bytes = B * 17 * 2 * 4; break;
+    case MPN_DEBUG_PERSON_BOX: src = h->person_box; bytes = n * 16; break;
+    case MPN_DEBUG_PERSON_IMAGE: src = h->person_img; bytes = n * 4; break;
+    default: return fail(h, MPN_ERR_INVALID_ARGUMENT, "unknown buffer %d", what);
+    }
+    if (bytes_out) *bytes_out = (int64_t)bytes;
+    if (!dst) return MPN_OK;                           // size query
+    if (capacity_bytes < 0) return fail(h, MPN_ERR_INVALID_ARGUMENT, "negative capacity");
+    if ((size_t)capacity_bytes < bytes) bytes = (size_t)capacity_bytes;
+    MPN_CUDA(h, cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return MPN_OK;
+}
+
+int mpn_test_sigmoid_monotone(mpn_handle *h, uint32_t key_begin, uint64_t count, uint64_t *violations, void *stream)
+{
+    if (!h || !violations) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    return launched(h, launch_test_monotone(key_begin, count, reinterpret_cast<unsigned long long *>(violations),
+                                            (cudaStream_t)stream), true, "test sigmoid monotone");
 }
 
 int mpn_debug_skip(mpn_handle *h, uint32_t mask)

@@ -112,14 +112,19 @@ int launch_set_pointer(const float **slot, const float *value, cudaStream_t s); 
 // after_candidates (optional): event recorded on `s` between the candidate scan and the sort / NMS kernel
 int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cudaEvent_t after_candidates = nullptr);
 
-int heatmap_chunks_per_image(int B, int hh, int ww);
+struct HeatmapWaves { int one_pass, minmax, norm; };   // resident CTA slots of the three heatmap-sized streaming kernels
+int heatmap_prepare(HeatmapWaves *w);                 // once per handle
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
-                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s);
+                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, int slots, cudaStream_t s);
 int launch_heatmap_head(const float *x, const float *w, const float *bias, int B, int hh, int ww, float *logits, float *kh,
                         float *seg, float *minmax_ws, float *minmax_out, int *partial_ws, unsigned int *counter_ws,
                         cudaStream_t s);
-int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s);
-// crop of the padded (20 floats / pixel) normalised workspace written by launch_normalise
+// the two-pass form (padded crop path): min / max from the logits, then activation + normalisation in one pass
+int launch_logit_minmax(const float *hml, int B, int hh, int ww, float *minmax_ws, int *partial_ws, int partial_chunks_cap,
+                        unsigned int *counter_ws, int slots, cudaStream_t s);
+int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const float *minmax_ws, float *nh,
+                        float *minmax_out, int slots, cudaStream_t s);
+// crop of the padded (20 floats / pixel) normalised map written by launch_heatmap_norm
 bool crop_padded_supported(int crop_h, int crop_w);
 int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,
                        int n_max, int crop_h, int crop_w, float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s);
@@ -129,9 +134,11 @@ int launch_crop(const float *kh, const float *minmax, int hh, int ww, const floa
 int launch_get_keypoints(const float *hm, int hh, int ww, double ymin, double xmin, double ymax, double xmax,
                          double threshold, int *out, cudaStream_t s);
 
-int kpdecode_prepare(cudaStream_t s);   // once per device before the first decode (bisects the exp == 1 threshold)
+// once per handle before the first decode: bisects the exp == 1 threshold, reports how many clusters are resident at once;
+// -2: crop size not covered by the decode kernel
+int kpdecode_prepare(cudaStream_t s, int crop_h, int crop_w, int *resident_clusters);
 int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
-                           float *scores, float *positions, int *argmax, cudaStream_t s);
+                           int resident_clusters, float *scores, float *positions, int *argmax, cudaStream_t s);
 
 struct PrnWeights {
     int D, hidden;
@@ -158,5 +165,6 @@ int launch_f32_to_bf16(const float *x, __nv_bfloat16 *y, const int *n_rows_dev, 
 int launch_transpose_to_bf16(const float *w, int rows, int cols, __nv_bfloat16 *wt, cudaStream_t s);
 
 int launch_test_math(const float *x, float *y, int64_t n, int which, cudaStream_t s);
+int launch_test_monotone(unsigned key_begin, unsigned long long count, unsigned long long *violations, cudaStream_t s);
 
 }  // namespace mpn

@@ -9,6 +9,14 @@ struct HostSlot {
     float *cls, *enc, *hml, *kh, *seg, *boxes, *scores, *kscores, *kpos;
     const float **enc_word;      // device word: where this call's box codes are (slot copy or the caller's pinned buffer)
     int *num, *offsets;
+    // The six small outputs (boxes, scores, keypoint_scores, keypoint_positions, num_boxes, person_offsets) are sub-ranges
+    // of ONE device block and come back in ONE copy into a pinned block of the same layout; mpn_wait hands them to the
+    // caller's buffers (a few tens of KB of host memcpy) -- three device-to-host copies per call instead of eight.
+    unsigned char *small_dev, *small_host;
+    size_t small_bytes;
+    struct { void *dst; size_t off, bytes; } scatter[6];
+    int n_scatter;
+    bool scatter_pending;
     cudaEvent_t ev_in, ev_comp, ev_out;
     bool used;
 };
@@ -51,7 +59,9 @@ struct mpn_handle {
     float *kh_ws;
     float *nh_ws;           // normalised heatmaps (create_pb.py:93-94), never returned
     float *minmax_ws;
-    int *hm_partial;        // [B, chunks, 17, 2] per-CTA (min, max) of the heatmap kernel
+    int *hm_partial;        // [B, chunks, 17, 2] per-CTA (min, max) of the heatmap kernels
+    int hm_partial_chunks;  // chunks per image the array holds
+    mpn::HeatmapWaves waves;
     unsigned int *hm_counter;   // [B] CTAs finished per image (self re-arming)
     // PRN workspace / weights
     float *crops_f32, *logits;
@@ -63,6 +73,7 @@ struct mpn_handle {
     void *fused;            // opaque: prn_fused.cu (NULL when the shape is not covered)
     void *big;              // opaque: prn_big.cu (NULL when the shape is not covered or the capacity is <= 256 persons)
     bool have_weights;
+    int decode_clusters;    // keypoint decode: clusters resident at once (kpdecode_prepare)
     // host path (mpn_submit_host): kHostSlots calls in flight, copy-in / compute / copy-out on three streams
     mpn::HostSlot slots[mpn::kHostSlots];
     cudaStream_t in_stream, out_stream;
@@ -72,6 +83,12 @@ struct mpn_handle {
     int64_t last_launches, total_launches;
     mpn::Profiler prof;
     bool prof_events_ready;
+    // what the most recent mpn_run left in the workspace (mpn_debug_fetch)
+    struct {
+        bool valid, padded;
+        int batch, hh, ww, n_max;
+        const float *prn_out;
+    } last_run;
 };
 
 namespace mpn {

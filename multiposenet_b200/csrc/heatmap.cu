@@ -256,43 +256,166 @@ __device__ __forceinline__ float normalise_tap(float v, float m, float d, float 
     return fmul(div_by_range(fsub(v, m), d, y), mask);
 }
 
-// create_pb.py:93-94 over the whole map: nh = (kh - m) / (M - m) * float(M > 0.2).  Normalising every heatmap pixel once
-// costs one division per pixel; normalising the four taps of every crop sample costs 4 N D divisions, which is 3x
-// (config 2) to 30x (crowded scenes) more.  The normalised map is a private workspace, so its pixels are PADDED to 20
-// floats (80 bytes): the crop kernel then fetches a tap's channels as aligned 16-byte vectors, 5 per pixel (it is bound
-// by L1 throughput and instruction issue; scalar taps cost 4x the load instructions and wavefronts).
-// One thread per (pixel, group of 4 channels); grid = (chunks, B).
-__global__ void __launch_bounds__(256) normalise_kernel(const float *__restrict__ kh, const float *__restrict__ minmax,
-                                                        const int npix, float *__restrict__ nh)
+// ---- the two-pass form used by mpn_run whenever the crops come from the padded normalised map -------------------------
+// The sigmoid recipe of mpn_math.cuh is monotone non-decreasing over ALL finite floats (walked exhaustively, 2^32 values:
+// tests/test_oracle_kat.py on the oracle's copy of the recipe, tests/test_gpu_parity.py on this one), so
+//     max over pixels of sigmoid(l) == sigmoid(max over pixels of l)     bit for bit, and the same for min.
+// Pass 1 (logit_minmax_kernel) therefore takes min / max of the raw LOGITS -- two instructions per value instead of the
+// ~35 of the bit-exact sigmoid, a pure HBM stream that runs beside the candidate scan -- and its last CTA per image
+// publishes (m, M) = (sigmoid(min), sigmoid(max)).  Pass 2 (heatmap_norm_kernel) then knows the range when it computes the
+// activations and writes all three products in one go: keypoint_heatmaps (create_pb.py:74), segmentation_masks (:75) and
+// the min-max normalised, masked map of create_pb.py:93-94 (padded to 20 floats per pixel for the crop kernel's 16-byte
+// taps).  This replaces activation + min / max in one kernel followed by a normalisation kernel that read the 17-channel
+// map back (13.9 MB at 640 x 640 x 8) and divided every value in a pass of its own.
+
+// order-preserving float <-> unsigned (atomicMin / atomicMax on possibly negative logits)
+__device__ __forceinline__ unsigned float_key(float f)
 {
-    __shared__ float s_m[kPadCh], s_d[kPadCh], s_mask[kPadCh], s_rcp[kPadCh];
-    const int img = blockIdx.y;
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+constexpr unsigned kKeyPosInf = 0xff800000u;       // float_key(+inf)
+constexpr unsigned kKeyNegInf = 0x007fffffu;       // float_key(-inf)
+
+__global__ void __launch_bounds__(kHmThreads) logit_minmax_kernel(const float *__restrict__ hml, const int npix,
+                                                                  const int tiles_per_img, unsigned *__restrict__ partial,
+                                                                  unsigned int *__restrict__ counter,
+                                                                  float *__restrict__ minmax)
+{
+    __shared__ unsigned s_min[kNK], s_max[kNK];
+    __shared__ int s_last;
+    const int img = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
-    pdl_wait();                                        // the heatmap kernel (min / max fold included) has completed
-    if (threadIdx.x < kPadCh) {
-        const bool real = threadIdx.x < kNK;
-        const float m = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2) : 0.0f;
-        const float M = real ? __ldg(minmax + ((size_t)img * kNK + threadIdx.x) * 2 + 1) : 1.0f;
-        const float d = fsub(M, m);
-        s_m[threadIdx.x] = m;
-        s_d[threadIdx.x] = d;
-        s_mask[threadIdx.x] = (real && M > 0.2f) ? 1.0f : 0.0f;
-        s_rcp[threadIdx.x] = range_rcp(d);
+    int ch[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ch[j] = (4 * tid + j) % kCH;
+    float mn[4], mx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mn[j] = __int_as_float(0x7f800000); mx[j] = -__int_as_float(0x7f800000); }
+    if (tid < kNK) { s_min[tid] = kKeyPosInf; s_max[tid] = kKeyNegInf; }
+    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
+    // four tiles per trip: four independent 16-byte loads in flight per thread (default caching: pass 2 re-reads the
+    // logits, from L2 whenever the call's maps fit)
+    for (int tile = blockIdx.x; tile < tiles_per_img; tile += 4 * gridDim.x) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = tile + u * gridDim.x;          // past the end: the trip's first tile again (min / max unchanged)
+            q[u] = __ldg(src + (size_t)(t < tiles_per_img ? t : tile) * kHmThreads + tid);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mn[j] = fminf(mn[j], v[j]); mx[j] = fmaxf(mx[j], v[j]); }
+        }
     }
     __syncthreads();
-    const float *src = kh + (size_t)img * npix * kNK;
-    float4 *dst = reinterpret_cast<float4 *>(nh + (size_t)img * npix * kPadCh);
-    const int total = npix * kGroups;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int p = i / kGroups, g = i - p * kGroups;
-        float o[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = 4 * g + k;
-            const float v = c < kNK ? __ldcg(src + (size_t)p * kNK + c) : 0.0f;
-            o[k] = c < kNK ? normalise_tap(v, s_m[c], s_d[c], s_rcp[c], s_mask[c]) : 0.0f;
+    for (int j = 0; j < 4; ++j) {
+        if (ch[j] < kNK) {
+            atomicMin(&s_min[ch[j]], float_key(mn[j]));
+            atomicMax(&s_max[ch[j]], float_key(mx[j]));
         }
-        dst[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    unsigned *my = partial + ((size_t)img * gridDim.x + blockIdx.x) * kNK * 2;
+    if (tid < kNK) { my[tid * 2] = s_min[tid]; my[tid * 2 + 1] = s_max[tid]; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counter + img, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < kNK) { s_min[tid] = kKeyPosInf; s_max[tid] = kKeyNegInf; }
+    __syncthreads();
+    if (tid < kNK * 8) {
+        const int c = tid % kNK, slice = tid / kNK;
+        unsigned lo = kKeyPosInf, hi = kKeyNegInf;
+        for (int i = slice; i < (int)gridDim.x; i += 8) {
+            const unsigned *q = partial + ((size_t)img * gridDim.x + i) * kNK * 2 + c * 2;
+            lo = min(lo, __ldcg(q)); hi = max(hi, __ldcg(q + 1));
+        }
+        atomicMin(&s_min[c], lo); atomicMax(&s_max[c], hi);
+    }
+    __syncthreads();
+    if (tid < kNK) {
+        // the monotone recipe: activations of the extreme logits ARE the extreme activations (create_pb.py:90,92)
+        minmax[((size_t)img * kNK + tid) * 2] = exact_sigmoidf(key_float(s_min[tid]));
+        minmax[((size_t)img * kNK + tid) * 2 + 1] = exact_sigmoidf(key_float(s_max[tid]));
+    }
+    if (tid == 0) counter[img] = 0u;
+}
+
+// Pass 2.  Same element-to-thread map as heatmap_kernel: thread t of a CTA always sees the channels (4 t + j) mod 18 of
+// its 64-pixel tiles, so the four channels' (m, M - m, 1 / (M - m), mask) live in registers; every element has one
+// precomputed destination per output (keypoint_heatmaps / segmentation_masks slot, normalised-map slot).  The first
+// trip's logits are requested before the wait on pass 1 (they do not depend on it).
+__global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float *__restrict__ hml, const int npix,
+                                                                     const int tiles_per_img, float *__restrict__ kh,
+                                                                     float *__restrict__ seg,
+                                                                     const float *__restrict__ minmax,
+                                                                     float *__restrict__ nh)
+{
+    const int img = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    bool is_kp[4];
+    int off[4], noff[4];                   // element offsets inside tile 0 of this image: 32-bit, four CTAs per SM
+    int ch[4];
+    float *kh_img = kh + (size_t)img * npix * kNK;
+    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
+    float *nh_img = nh + (size_t)img * npix * kPadCh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = 4 * tid + j, p = e / kCH;
+        ch[j] = e - p * kCH;
+        is_kp[j] = ch[j] < kNK;
+        off[j] = is_kp[j] ? p * kNK + ch[j] : p;
+        noff[j] = p * kPadCh + ch[j];
+    }
+    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
+    int tile = blockIdx.x;
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+    if (tile < tiles_per_img) {
+        qa = __ldcs(src + (size_t)tile * kHmThreads + tid);
+        if (tile + (int)gridDim.x < tiles_per_img) qb = __ldcs(src + (size_t)(tile + gridDim.x) * kHmThreads + tid);
+    }
+    pdl_wait();                                        // pass 1 (min / max) has completed
+    float m[4], d[4], rcp[4], mask[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float lo = is_kp[j] ? __ldg(minmax + ((size_t)img * kNK + ch[j]) * 2) : 0.0f;
+        const float hi = is_kp[j] ? __ldg(minmax + ((size_t)img * kNK + ch[j]) * 2 + 1) : 1.0f;
+        m[j] = lo;
+        d[j] = fsub(hi, lo);
+        rcp[j] = range_rcp(d[j]);
+        mask[j] = hi > 0.2f ? 1.0f : 0.0f;
+    }
+    for (; tile < tiles_per_img; tile += 2 * gridDim.x) {
+        const int tile2 = tile + gridDim.x;
+        const bool two = tile2 < tiles_per_img;
+        const float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
+        // next trip's loads in flight while this one is evaluated
+        const int nt = tile + 2 * gridDim.x, nt2 = nt + gridDim.x;
+        if (nt < tiles_per_img) qa = __ldcs(src + (size_t)nt * kHmThreads + tid);
+        if (nt2 < tiles_per_img) qb = __ldcs(src + (size_t)nt2 * kHmThreads + tid);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float sa, sb;
+            exact_sigmoidf_pair(va[j], vb[j], sa, sb);
+            if (is_kp[j]) {
+                kh_img[(size_t)tile * (kHmPix * kNK) + off[j]] = sa;
+                nh_img[(size_t)tile * (kHmPix * kPadCh) + noff[j]] = normalise_tap(sa, m[j], d[j], rcp[j], mask[j]);
+                if (two) {
+                    kh_img[(size_t)tile2 * (kHmPix * kNK) + off[j]] = sb;
+                    nh_img[(size_t)tile2 * (kHmPix * kPadCh) + noff[j]] = normalise_tap(sb, m[j], d[j], rcp[j], mask[j]);
+                }
+            } else if (seg_img) {
+                seg_img[(size_t)tile * kHmPix + off[j]] = va[j];
+                if (two) seg_img[(size_t)tile2 * kHmPix + off[j]] = vb[j];
+            }
+        }
     }
 }
 
@@ -551,37 +674,42 @@ __global__ void minmax_copy_kernel(const float *ws, float *out, int n)
 
 }  // namespace
 
-int heatmap_chunks_per_image(int B, int hh, int ww)
+// Resident CTA slots (CTAs per SM x SMs) of the three 288-thread streaming kernels on this handle's device.
+int heatmap_prepare(HeatmapWaves *w)
 {
-    // Two 64-pixel tiles per trip, and at most ONE resident wave of CTAs: 4 CTAs of 288 threads fit an SM (registers), and
-    // a grid of 1.35 or 1.5 waves costs two full rounds of trips (measured: 800 CTAs x 2 trips at 640x640x8 took as long
-    // as 4 trips).  The wave leaves room for the B single-CTA sort / NMS blocks that run beside this kernel (an SM that
-    // holds one of them still takes two heatmap CTAs).  Small calls end up with one trip per CTA.
-    static int slots = 0;
-    if (slots == 0) {
-        int per_sm = 0, sms = 0, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heatmap_kernel, kHmThreads, 0) != cudaSuccess) per_sm = 0;
-        cudaGetLastError();
-        slots = per_sm > 0 && sms > 0 ? per_sm * sms : 4 * 148;
-    }
-    const int tiles = (hh * ww + kHmPix - 1) / kHmPix;
-    int budget = slots - 2 * (B < 148 ? B : 148);
-    int cap = budget / B;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return -1;
+    int a = 0, b = 0, c = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, heatmap_kernel, kHmThreads, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, logit_minmax_kernel, kHmThreads, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, heatmap_norm_kernel, kHmThreads, 0) != cudaSuccess || a < 1 || b < 1 ||
+        c < 1)
+        return -1;
+    w->one_pass = a * sms; w->minmax = b * sms; w->norm = c * sms;
+    return 0;
+}
+
+// Chunks per image of a heatmap-sized streaming grid: at most ONE resident wave of CTAs (`slots`) -- a grid of 1.35 or 1.5
+// waves costs two full rounds of trips (measured: 800 CTAs x 2 trips at 640 x 640 x 8 took as long as 4 trips) -- minus room
+// for the B single-CTA sort / NMS blocks that run beside it (an SM that holds one of them still takes two of these CTAs);
+// `tiles_per_trip` 64-pixel tiles per CTA and trip.  Small calls end up with one trip per CTA.
+static int wave_chunks_per_image(int slots, int B, int tiles, int tiles_per_trip)
+{
+    int cap = (slots - 2 * (B < 148 ? B : 148)) / B;
     if (cap < 1) cap = 1;
-    const int trips = (tiles + 2 * cap - 1) / (2 * cap);
-    const int per_img = (tiles + 2 * trips - 1) / (2 * trips);
+    const int trips = (tiles + tiles_per_trip * cap - 1) / (tiles_per_trip * cap);
+    const int per_img = (tiles + tiles_per_trip * trips - 1) / (tiles_per_trip * trips);
     return per_img < 1 ? 1 : per_img;
 }
 
 int launch_heatmaps(const float *hml, int B, int hh, int ww, float *kh, float *seg, float *minmax_ws,
-                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, cudaStream_t s)
+                    float *minmax_out, int *partial_ws, unsigned int *counter_ws, int slots, cudaStream_t s)
 {
     const int npix = hh * ww;
     const int tiles = (npix + kHmPix - 1) / kHmPix;
     int launches = 0;
-    dim3 grid(heatmap_chunks_per_image(B, hh, ww), B);
+    dim3 grid(wave_chunks_per_image(slots, B, tiles, 2), B);
     prof_mark(s, "heatmap");
     heatmap_kernel<<<grid, kHmThreads, 0, s>>>(hml, npix, tiles, kh, seg, partial_ws, counter_ws,
                                                reinterpret_cast<int *>(minmax_ws));
@@ -602,7 +730,7 @@ int launch_heatmap_head(const float *x, const float *w, const float *bias, int B
     if (npix % kHeadPix != 0) return -(int)cudaErrorInvalidValue;     // true for every image that is a multiple of 128
     const int tiles = npix / kHeadPix;
     int launches = 0;
-    // the partial array is sized for heatmap_chunks_per_image() <= ceil(npix / 128) chunks: tiles <= that
+    // the partial array holds ceil(npix / 128) chunks per image: tiles <= that
     int per_img = (148 * 6 + B - 1) / B;
     if (per_img > tiles) per_img = tiles;
     dim3 grid(per_img, B);
@@ -618,15 +746,34 @@ int launch_heatmap_head(const float *x, const float *w, const float *bias, int B
     return launches;
 }
 
-int launch_normalise(const float *kh, const float *minmax, int B, int hh, int ww, float *nh, cudaStream_t s)
+// pass 1 of the two-pass form: (min, max) of the activations from the min / max of the logits -> minmax_ws [B, 17, 2]
+int launch_logit_minmax(const float *hml, int B, int hh, int ww, float *minmax_ws, int *partial_ws, int partial_chunks_cap,
+                        unsigned int *counter_ws, int slots, cudaStream_t s)
 {
-    const int total = hh * ww * kGroups;
-    int per_img = (148 * 8 + B - 1) / B;
-    const int max_blocks = (total + 255) / 256;
-    if (per_img > max_blocks) per_img = max_blocks;
-    prof_mark(s, "normalise");
-    launch_k(normalise_kernel, dim3(per_img, B), dim3(256), 0, s, true, kh, minmax, hh * ww, nh);
+    const int npix = hh * ww, tiles = (npix + kHmPix - 1) / kHmPix;
+    int per_img = wave_chunks_per_image(slots, B, tiles, 4);
+    if (per_img > partial_chunks_cap) per_img = partial_chunks_cap;
+    prof_mark(s, "logit_minmax");
+    logit_minmax_kernel<<<dim3(per_img, B), kHmThreads, 0, s>>>(hml, npix, tiles, reinterpret_cast<unsigned *>(partial_ws),
+                                                                counter_ws, minmax_ws);
     return 1;
+}
+
+// pass 2: keypoint_heatmaps, segmentation_masks and the padded normalised map in one pass over the logits
+int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const float *minmax_ws, float *nh,
+                        float *minmax_out, int slots, cudaStream_t s)
+{
+    const int npix = hh * ww, tiles = (npix + kHmPix - 1) / kHmPix;
+    const int per_img = wave_chunks_per_image(slots, B, tiles, 2);
+    int launches = 1;
+    prof_mark(s, "heatmap_norm");
+    launch_k(heatmap_norm_kernel, dim3(per_img, B), dim3(kHmThreads), 0, s, true, hml, npix, tiles, kh, seg, minmax_ws, nh);
+    if (minmax_out) {
+        const int nmm = B * kNK * 2;
+        minmax_copy_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(minmax_ws, minmax_out, nmm);
+        ++launches;
+    }
+    return launches;
 }
 
 int launch_crop(const float *src, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,

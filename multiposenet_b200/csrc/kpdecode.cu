@@ -26,11 +26,11 @@
 // test).  keypoint_scores = 1 / S is held to 1e-4 only, so the terms use the hardware ex2 approximation.
 //
 // The peers write their per-channel partials straight into CTA 0's shared memory (distributed shared memory), then the
-// cluster barrier, then CTA 0 merges and stores.  Two kernels share this arithmetic: keypoint_decode_kernel, one cluster
-// per person with the logits loaded straight into registers (lowest latency, few persons), and
-// keypoint_decode_stream_kernel, PERSISTENT clusters that walk the persons with every CTA's slab arriving by one bulk
-// copy (TMA) into a two-slot shared-memory ring, two CTAs per SM, so that the next person's bytes are in flight while
-// the current one is reduced (many persons: HBM bound).
+// cluster barrier, then CTA 0 merges and stores.  keypoint_decode_stream_kernel: PERSISTENT clusters that walk the persons
+// with every CTA's slab arriving by one bulk copy (TMA) into a two-slot shared-memory ring, two CTAs per SM, so that the
+// next person's bytes are in flight while the current one is reduced.  (A second kernel with one cluster per person and
+// the logits loaded straight into registers was measured slower at every person count and is gone; every crop size the
+// handle accepts -- 17 * positions a multiple of 32 -- satisfies the bulk copy's 16-byte granularity.)
 #include <cstdlib>
 
 #include "common.cuh"
@@ -216,34 +216,6 @@ __device__ __forceinline__ void cluster_finish(const ClusterStats &st, int buf, 
     }
 }
 
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
-keypoint_decode_kernel(const float *__restrict__ logits, const int *__restrict__ n_dev, const int n_host, const int crop_h,
-                       const int crop_w, float *__restrict__ scores, float *__restrict__ positions,
-                       int *__restrict__ argmax_out)
-{
-    __shared__ BlockScratch sc;
-    __shared__ ClusterStats stats;        // used in CTA 0 only
-    const int n = blockIdx.x / kCluster;
-    const unsigned rank = cluster_rank();
-    pdl_trigger();
-    pdl_wait();                           // the PRN has completed
-    const int N = n_dev ? *n_dev : n_host;
-    if (n >= N) return;                   // uniform over the cluster
-    const int P = crop_h * crop_w;
-    const int per = (P + kCluster - 1) / kCluster;
-    const int p0 = (int)rank * per, p1 = min(P, p0 + per);
-    const int tid = threadIdx.x, c = tid % kNK, q = tid / kNK;
-    const float *person = logits + (size_t)n * P * kNK;
-    const float *row = person + (size_t)p0 * kNK;
-    float v[kMaxPerThread];
-#pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i)
-        v[i] = (p0 + q + kLanes * i < p1) ? __ldcs(row + (size_t)tid + (size_t)kThreads * i) : -__int_as_float(0x7f800000);
-    slab_partials(v, p0, q, c, tid >> 5, tid & 31, g_exp_one_x0, sc, peer_shared(&stats, 0), 0, rank);
-    cluster_sync_all();                   // all partials have landed in CTA 0; the peers are done
-    if (rank == 0) cluster_finish(stats, 0, sc, person, P, n, crop_h, crop_w, g_exp_one_x0, scores, positions, argmax_out);
-}
-
 // ---- streaming variant ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -336,43 +308,35 @@ keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__res
 
 }  // namespace
 
-int kpdecode_prepare(cudaStream_t s)
+int kpdecode_prepare(cudaStream_t s, int crop_h, int crop_w, int *resident_clusters)
 {
     exp_one_threshold_kernel<<<1, 1, 0, s>>>();
     if (cudaGetLastError() != cudaSuccess) return -1;
     // the streaming kernel's slab ring: sized for the default 56 x 36 crop and anything smaller
-    return cudaFuncSetAttribute(keypoint_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kStreamSlabBytes) == cudaSuccess ? 0 : -1;
+    if (cudaFuncSetAttribute(keypoint_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSlabBytes) !=
+        cudaSuccess)
+        return -1;
+    const int P = crop_h * crop_w, per = (P + kCluster - 1) / kCluster;
+    if (P > kMaxPerThread * kLanes * kCluster || per % 4 != 0 || P % 4 != 0 || kSlots * per * kNK * 4 > kStreamSlabBytes) return -2;
+    // clusters that fit the device at once (per handle: the launch grid is min(persons, this))
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSlots * per * kNK * 4;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel, &cfg) != cudaSuccess || n < 1) n = 64;
+    cudaGetLastError();
+    *resident_clusters = n;
+    return 0;
 }
 
 int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, int n_max, int crop_h, int crop_w,
-                           float *scores, float *positions, int *argmax, cudaStream_t s)
+                           int resident_clusters, float *scores, float *positions, int *argmax, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
-    if (crop_h * crop_w > kMaxPerThread * kLanes * kCluster) return -(int)cudaErrorInvalidValue;
     const int P = crop_h * crop_w, per = (P + kCluster - 1) / kCluster;
-    static const char *force = getenv("MPN_TUNE_DECODE");      // development: "0" register kernel, "1" streaming kernel
-    const bool stream_ok = (per % 4 == 0) && (P % 4 == 0) && kSlots * per * kNK * 4 <= kStreamSlabBytes;
-    const bool want_stream = force ? force[0] == '1' : true;   // measured faster at every person count (94.5 vs 96.1 us per c2 step)
-    if (stream_ok && want_stream) {
-        static int resident = 0;          // clusters that fit the device at once
-        if (resident == 0) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSlots * per * kNK * 4;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel, &cfg) != cudaSuccess || n < 1) n = 64;
-            cudaGetLastError();
-            resident = n;
-        }
-        const int clusters = n_max < resident ? n_max : resident;
-        prof_mark(s, "keypoint_decode");
-        launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)(kSlots * per * kNK * 4), s, true,
-                 logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
-        return 1;
-    }
+    const int clusters = n_max < resident_clusters ? n_max : resident_clusters;
     prof_mark(s, "keypoint_decode");
-    launch_k(keypoint_decode_kernel, dim3(n_max * kCluster), dim3(kThreads), 0, s, true, logits, n_dev, n_host, crop_h, crop_w,
-             scores, positions, argmax);
+    launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)(kSlots * per * kNK * 4), s, true,
+             logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
     return 1;
 }
 

@@ -241,7 +241,9 @@ class Detector:
         if key not in self._dev_out:
             dev, f32, i32 = self.device, torch.float32, torch.int32
             h4, w4, NP = H // 4, W // 4, B * max_det
-            self._dev_out = {key: {
+            if len(self._dev_out) >= 8:         # a caller cycling through many shapes: keep the most recent few
+                self._dev_out.pop(next(iter(self._dev_out)))
+            self._dev_out[key] = {
                 "boxes": torch.zeros((B, max_det, 4), dtype=f32, device=dev),
                 "scores": torch.zeros((B, max_det), dtype=f32, device=dev),
                 "num_boxes": torch.zeros((B,), dtype=i32, device=dev),
@@ -250,7 +252,7 @@ class Detector:
                 "keypoint_scores": torch.zeros((NP, 17), dtype=f32, device=dev),
                 "keypoint_positions": torch.zeros((NP, 17, 2), dtype=f32, device=dev),
                 "person_offsets": torch.zeros((B + 1,), dtype=i32, device=dev),
-            }}
+            }
         return self._dev_out[key]
 
     def run_device(self, encoded_boxes, class_logits, heatmap_logits, image_hw=None, score_threshold=None,
@@ -392,6 +394,34 @@ class Detector:
                                            self._stream()))
         return kh, seg, mm
 
+    def heatmaps_normalised(self, heatmap_logits):
+        """create_pb.py:73-76 + :90-94 in the two-pass form of the full path (min / max from the logits, then one pass)
+        -> (keypoint_heatmaps, segmentation_masks, minmax [B,17,2], normalised [B,h,w,20]; channels 17..19 are padding)."""
+        B, h, w, _ = heatmap_logits.shape
+        dev = self.device
+        kh = torch.empty((B, h, w, 17), dtype=torch.float32, device=dev)
+        seg = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        mm = torch.empty((B, 17, 2), dtype=torch.float32, device=dev)
+        nh = torch.zeros((B, h, w, 20), dtype=torch.float32, device=dev)
+        self._check(self._lib.mpn_heatmaps_normalised(self._handle, _ptr(heatmap_logits), B, h, w, _ptr(kh), _ptr(seg), _ptr(mm),
+                                                      _ptr(nh), self._stream()))
+        return kh, seg, mm, nh
+
+    def crop_padded(self, normalised, boxes, box_ind):
+        """create_pb.py:106-109 on a normalised map: [B,h,w,17] (padded here) or already padded [B,h,w,20]
+        -> (crops f32 [N,56,36,17], the same crops in bfloat16), by the crop kernel the full path uses."""
+        if normalised.shape[-1] == 17:
+            normalised = torch.nn.functional.pad(normalised, (0, 3)).contiguous()
+        B, h, w, _ = normalised.shape
+        N = int(boxes.shape[0])
+        ch, cw = self.config.crop_size
+        f = torch.empty((N, ch, cw, 17), dtype=torch.float32, device=self.device)
+        b = torch.empty((N, ch, cw, 17), dtype=torch.bfloat16, device=self.device)
+        if N:
+            self._check(self._lib.mpn_crop_padded(self._handle, _ptr(normalised), B, h, w, _ptr(boxes), _ptr(box_ind), N,
+                                                  _ptr(f), _ptr(b), self._stream()))
+        return f, b
+
     def heatmap_head(self, features, weight, bias, want_logits=True):
         """detector/keypoint_subnet.py:49-58 (1x1 conv 64 -> 18 + bias, NCHW -> NHWC) fused with heatmaps():
         features [B,64,h,w] CUDA f32 -> (heatmap_logits [B,h,w,18] or None, keypoint_heatmaps, segmentation_masks, minmax)."""
@@ -459,6 +489,24 @@ class Detector:
         y = torch.empty_like(x)
         self._check(self._lib.mpn_test_sigmoid(self._handle, _ptr(x), _ptr(y), x.numel(), self._stream()))
         return y
+
+    def sigmoid_monotone_violations(self, key_begin=0, count=1 << 32):
+        """Test hook (mpn_test_sigmoid_monotone): neighbouring floats x < x' with sigmoid(x) > sigmoid(x') -- or on which
+        the packed-pair form of the recipe differs from the scalar one -- among `count` floats in increasing order."""
+        counter = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._check(self._lib.mpn_test_sigmoid_monotone(self._handle, int(key_begin), int(count), _ptr(counter), self._stream()))
+        return int(counter.item())
+
+    def debug_fetch(self, what):
+        """Test hook (mpn_debug_fetch): one internal buffer of the most recent run_device / submit_host as a CUDA tensor
+        ("normalised", "crops_f32", "crops_bf16", "logits", "minmax", "person_box", "person_image")."""
+        code = _lib.DEBUG_BUFFERS[what]
+        n = C.c_int64(0)
+        self._check(self._lib.mpn_debug_fetch(self._handle, code, None, 0, C.byref(n)))
+        dtype = {"crops_bf16": torch.bfloat16, "person_image": torch.int32}.get(what, torch.float32)
+        out = torch.empty((n.value // torch.empty((), dtype=dtype).element_size(),), dtype=dtype, device=self.device)
+        self._check(self._lib.mpn_debug_fetch(self._handle, code, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def set_profiling(self, enable=True):
         """Per-kernel CUDA-event timing of run_device / run_host_async (bench.py's roofline leg)."""

@@ -46,6 +46,7 @@ def lib():
         _lib.orc_nms.restype = C.c_int
         _lib.orc_detector_filter.restype = C.c_int
         _lib.orc_version.restype = C.c_int
+        _lib.orc_sigmoid_monotone_violations.restype = C.c_int64
     return _lib
 
 
@@ -71,6 +72,11 @@ def sigmoidf(x):
     y = np.empty_like(x)
     lib().orc_sigmoidf_array(_fp(x), _fp(y), C.c_int64(x.size))
     return y
+
+
+def sigmoid_monotone_violations(key_begin=0, count=1 << 32):
+    """Neighbouring floats x < x' with sigmoid(x) > sigmoid(x') among `count` pairs in increasing order (0 = monotone)."""
+    return int(lib().orc_sigmoid_monotone_violations(C.c_uint32(key_begin), C.c_uint64(count)))
 
 
 def round_bf16(x):

@@ -43,6 +43,29 @@ ORC_API void orc_sigmoidf_array(const float *x, float *y, int64_t n)
     for (int64_t i = 0; i < n; ++i) y[i] = orc_sigmoidf(x[i]);
 }
 
+/* Walks `count` neighbouring float pairs (x, next float above x) in increasing order from ordered key `key_begin`
+ * (keys below 2^31: negative floats, bits ~key; the rest: positive floats, bits key - 2^31) and counts pairs of finite
+ * floats with sigmoid(x) > sigmoid(next): the recipe is monotone iff the count over all 2^32 - 1 pairs is 0.  The product
+ * relies on that (min / max of the activations from the min / max of the logits, create_pb.py:90,92). */
+ORC_API int64_t orc_sigmoid_monotone_violations(uint32_t key_begin, uint64_t count)
+{
+    int64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+    for (int64_t blk = 0; blk < (int64_t)((count + 65535) / 65536); ++blk) {
+        uint64_t i0 = (uint64_t)blk * 65536, i1 = i0 + 65536 < count ? i0 + 65536 : count;
+        for (uint64_t i = i0; i < i1; ++i) {
+            uint64_t k = (uint64_t)key_begin + i;
+            if (k + 1 > 0xffffffffull) break;
+            uint32_t k0 = (uint32_t)k, k1 = (uint32_t)(k + 1);
+            float x0 = orc_bits_to_float((k0 & 0x80000000u) ? (k0 & 0x7fffffffu) : ~k0);
+            float x1 = orc_bits_to_float((k1 & 0x80000000u) ? (k1 & 0x7fffffffu) : ~k1);
+            if (!(fabsf(x0) <= 3.4028234e38f) || !(fabsf(x1) <= 3.4028234e38f)) continue;
+            bad += orc_sigmoidf(x0) > orc_sigmoidf(x1);
+        }
+    }
+    return bad;
+}
+
 ORC_API void orc_round_bf16_array(const float *x, float *y, int64_t n)
 {
     for (int64_t i = 0; i < n; ++i) y[i] = orc_round_bf16(x[i]);

@@ -414,7 +414,7 @@ def test_keypoint_decode_near_ties_take_the_exact_rescan(det6):
     rule (first index of the maximal fp32 probability) then picks the earlier position even when it holds the smaller
     logit.  The one-pass decode flags such channels and rescans them exactly."""
     rng = np.random.default_rng(5)
-    for n in (6, 170):                                  # register kernel, streaming kernel
+    for n in (6, 170):                                  # fewer / more persons than resident clusters
         logits = rng.normal(-3.0, 0.5, (n, 56, 36, 17)).astype(np.float32)
         cases = [(0, 0, 0.3, 1), (1, 3, 0.3, 2), (2, 5, 0.1, 1), (3, 7, 0.01, 3), (4, 16, 0.45, 1), (5, 9, 0.02, 40)]
         for person, ch, mx, ulps in cases:
@@ -494,6 +494,15 @@ def _full_case(det, wl, inp, prn_weights, mode, host):
     assert decided.mean() > 0.5
     wrong = (kp != want["keypoint_positions"]).any(-1) & decided
     assert not wrong.any(), f"{int(wrong.sum())} keypoint argmax mismatches among {int(decided.sum())} decided"
+    # ... and NO keypoint is exempt: where the oracle's top-2 gap is inside the PRN's tolerance the device may pick another
+    # position, but only one whose oracle logit is within that tolerance of the oracle's maximum (a legitimate near-tie)
+    flat = want["logits"].reshape(N, 56 * 36, 17)
+    yx = np.rint(kp * np.array([56, 36], np.float32)).astype(np.int64)
+    at_dev = np.take_along_axis(flat, (yx[..., 0] * 36 + yx[..., 1])[:, None, :], 1)[:, 0]
+    short = (flat.max(1) - at_dev) / np.abs(flat).max((1, 2))[:, None]
+    differ = (kp != want["keypoint_positions"]).any(-1)
+    print(f"{mode}: {int(differ.sum())} of {differ.size} keypoints differ from the oracle's argmax, worst shortfall {short.max():.2e}")
+    assert short.max() <= 2 * (RTOL_FP32 if mode == "fp32" else RTOL_BF16), f"shortfall {short.max():.2e}"
     tol = RTOL_FP32 if mode == "fp32" else RTOL_BF16
     np.testing.assert_allclose(ks[decided], want["keypoint_scores"][decided], rtol=50 * tol, atol=1e-7)
     return got, want

@@ -222,3 +222,51 @@ def test_lanes_interleaved_calls_reproduce_the_lone_detector(det_c2, weights):
                 _eq(a, b, f"set {i}: {k}")
     finally:
         lanes.close()
+
+
+def test_lanes_stress_many_queued_calls_mixed_person_counts(weights):
+    """Robustness of the cooperative single-kernel PRN (hand-rolled grid barrier on a never-reset counter), programmatic
+    dependent launch and graph replay under load: 4 lanes x 5 000 calls queued without a host synchronisation, the calls
+    cycling through batches with 0 persons (every grid exits on the device-side count), ~120 persons (single-kernel PRN)
+    and > 256 persons (large-batch kernels).  Sampled results must be the bits of a lone handle."""
+    from multiposenet_b200 import Detector, DetectorConfig, DetectorLanes
+    wl = synthetic.WORKLOADS["c3"]
+    cfg = DetectorConfig(max_batch=3, max_height=640, max_width=640, max_boxes=128, score_threshold=0.3, iou_threshold=0.5,
+                         scale_multipliers=wl.multipliers, prn_mode="bf16", prn_modes_allocated=("bf16",))
+    crowd = synthetic.make_inputs(wl, batch=3)
+    one = {k: np.ascontiguousarray(crowd[k][:1]) for k in ("class_logits", "encoded_boxes", "heatmap_logits")}
+    none = dict(crowd, class_logits=np.full_like(crowd["class_logits"], -9.0))
+    kinds = [none, one, crowd]
+    names = ("boxes", "scores", "num_boxes", "keypoint_scores", "keypoint_positions", "person_offsets")
+    lone = Detector(weights, cfg)
+    try:
+        alone = [_run(lone, k) for k in kinds]
+    finally:
+        lone.close()
+    counts = [int(a["person_offsets"][-1]) for a in alone]
+    assert counts[0] == 0 and 0 < counts[1] <= 256 < counts[2]
+    dev = [{k: _cuda(s[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")} for s in kinds]
+    n_lanes, per_lane = 4, 5000
+    lanes = DetectorLanes(weights, cfg, lanes=n_lanes)
+    try:
+        lanes.fork()
+        snaps = []
+        for i in range(n_lanes * per_lane):
+            kind = (i // n_lanes + i % n_lanes) % 3          # every lane sees every kind, neighbours differ
+            d = dev[kind]
+            lane, out = lanes.submit(d["encoded_boxes"], d["class_logits"], d["heatmap_logits"])
+            if i % 1777 == 0 or i >= n_lanes * (per_lane - 1):
+                with torch.cuda.stream(lanes.streams[lane]):
+                    snaps.append((kind, {k: out[k].clone() for k in names}))
+        lanes.join()
+        torch.cuda.synchronize()
+        assert len(snaps) >= 12
+        for kind, snap in snaps:
+            n = counts[kind]
+            for k in names:
+                a, b = snap[k].cpu().numpy(), alone[kind][k]
+                if k in ("keypoint_scores", "keypoint_positions"):
+                    a, b = a[:n], b[:n]
+                _eq(a, b, f"kind {kind}: {k}")
+    finally:
+        lanes.close()

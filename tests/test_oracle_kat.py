@@ -30,6 +30,15 @@ def test_exp_recipe_accuracy_and_edges():
                   (1 / (1 + np.exp(-xs.astype(np.float64))))) < 3e-7
 
 
+def test_sigmoid_recipe_is_monotone_over_all_floats():
+    """Exhaustive: every pair of neighbouring finite floats.  The product takes min / max of the heatmap LOGITS and applies
+    the sigmoid to the two extremes (create_pb.py:90,92 ask for min / max of the activations): identical bits iff the
+    recipe never decreases."""
+    assert oracle.sigmoid_monotone_violations(0, 1 << 32) == 0
+    e = oracle.sigmoidf(f32([-104.0, -103.0, -88.0, -87.5, -87.0, 0.0, 16.0, 17.0, 88.0, 200.0]))
+    assert (np.diff(e) >= 0).all()
+
+
 def test_bf16_rounding():
     x = f32([1.0, 1.00390625, 1.005859375, -2.5, 3.0e38, 1e-40, np.inf])
     y = oracle.round_bf16(x)
