@@ -88,6 +88,11 @@ def parse_args():
     ap.add_argument("--prn-mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs the workload's batch; strong: the workload's batch is split over the ranks "
+                         "(BASELINE configs[3]: 1024x1024, 64 images over 2/4/8 GPUs)")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="the K-step timed block is repeated until this much device time has been measured")
     ap.add_argument("--lanes", type=int, default=3,
                     help="Detector handles / CUDA streams fed round-robin in the device-resident leg (DetectorLanes)")
     return ap.parse_args()
@@ -159,24 +164,24 @@ def set_bytes(inp):
 
 
 def algorithmic_bytes(kernel, wl, B, n_persons, n_cand, mode):
-    """Compulsory HBM traffic of one launch ('Kernels and their rooflines')."""
+    """(compulsory, moved) HBM bytes of one launch.  `compulsory` follows SURVEY.md section 8(d): every input byte once,
+    every output byte once, nothing that exists only because of how the path is cut into kernels (None for a kernel that
+    is such an extra pass); `moved` is what the kernel as built has to read + write ('Kernels and their
+    rooflines')."""
     A, pix = wl.num_anchors, (wl.height // 4) * (wl.width // 4)
-    wbytes = 2 if mode == "bf16" else 4
+    w2 = 2 * D * HIDDEN * (2 if mode == "bf16" else 4) + (HIDDEN + D) * 4          # both weight matrices + biases
     table = {
-        "candidates_flat": 4 * A * B + 8 * n_cand,
-        "sort_nms": 8 * n_cand + 16 * n_cand + B * wl.max_detections * 20,
-        "heatmap": 72 * pix * B + 72 * pix * B,
-        "crop": n_persons * D * (4 + (2 if mode == "bf16" else 0)),
-        # both weight matrices once, x in bf16, residual read and logits written (in place); launched but idle above 256 persons
-        "prn_fused": None if n_persons > 256 else 2 * D * HIDDEN * 2 + n_persons * D * (2 + 4 + 4),
-        "prn_bf16_fc1": D * HIDDEN * 2 + n_persons * D * 2,
-        "prn_bf16_fc2": D * HIDDEN * 2 + n_persons * (HIDDEN * 2 + D * 4 + D * 4),
-        "prn_fp32_fc1": D * HIDDEN * 4 + n_persons * D * 4,
-        "prn_fp32_fc2": D * HIDDEN * 4 + n_persons * (HIDDEN * 4 + D * 4 + D * 4),
-        "keypoint_decode": n_persons * D * 4,
+        "candidates_flat": (4 * A * B + 8 * n_cand, 4 * A * B + 8 * n_cand),
+        "sort_nms": (24 * n_cand + B * wl.max_detections * 20, 24 * n_cand + B * wl.max_detections * 40),
+        "heatmap": (144 * pix * B, 144 * pix * B),                        # one-pass kernel (per-tap crop path)
+        "logit_minmax": (None, 72 * pix * B),                             # extra pass over the logits (L2-resident re-read later)
+        "heatmap_norm": (144 * pix * B, (144 + 80) * pix * B),            # + the padded normalised map (workspace)
+        "crop": (n_persons * D * 4, n_persons * D * (4 + (2 if mode == "bf16" else 0))),
+        # section 8(d): weights once + (unfused) crops in and logits out; the bf16 copy of x is an artefact of the cut
+        "prn_fused": (None, None) if n_persons > 256 else (w2 + n_persons * D * 8, w2 + n_persons * D * 10),
+        "keypoint_decode": (n_persons * D * 4, n_persons * D * 4),
     }
-    del wbytes
-    return table.get(kernel)
+    return table.get(kernel, (None, None))
 
 
 # ------------------------------------------------------------------------------------------------- CPU leg
@@ -208,8 +213,8 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_leg(wl, weights, ring, seconds, max_steps=None, warmup=2):
-    run = cpu_port_runner(wl, weights)
+def run_cpu_leg(wl, weights, ring, seconds, max_steps=None, warmup=2, run=None):
+    run = run or cpu_port_runner(wl, weights)
     for i in range(warmup):
         run(ring[i % len(ring)])
     n, t0 = 0, time.perf_counter()
@@ -229,21 +234,38 @@ def run_cpu_leg(wl, weights, ring, seconds, max_steps=None, warmup=2):
             "ms_per_step": 1e3 * total / n, "steps": n}
 
 
+def batch_per_gpu(wl, args):
+    """weak: every rank runs the workload's batch; strong: the batch is split over the ranks (contiguous image blocks)."""
+    if args.scaling == "strong":
+        if wl.batch % args.gpus != 0:
+            raise SystemExit(f"--scaling strong: batch {wl.batch} is not divisible by {args.gpus} GPUs")
+        return wl.batch // args.gpus
+    return wl.batch
+
+
 def reference_arm(args, wl, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.15 (the reference's only
-    backend) cannot be installed here (no network, no cp312 wheel), so this times the oracle port."""
+    backend) cannot be installed here (no network, no cp312 wheel), so this times the oracle port.  One host CPU runs the
+    per-GPU batch of the other arm (same config); at N > 1 rank 0 alone runs it."""
     if rank != 0:
         return
     from multiposenet_b200 import synthetic
     weights = synthetic.make_prn_weights()
-    ring = make_ring(wl, 2, 0)
+    B = batch_per_gpu(wl, args)
+    ring = [synthetic.make_inputs(wl, replicate=r, batch=B) for r in range(2)]
     steps = max(1, min(args.steps, 400))
-    res = run_cpu_leg(wl, weights, ring, seconds=0, max_steps=steps, warmup=max(1, min(args.warmup, 5)))
+    # warm for at least a second (thread pools, page faults, BLAS buffers: 20 cold steps once read 584 instead of ~690 images/s)
+    run = cpu_port_runner(wl, weights)
+    t0, n_warm = time.perf_counter(), 0
+    while n_warm < max(1, min(args.warmup, 5)) or time.perf_counter() - t0 < 1.0:
+        run(ring[n_warm % 2])
+        n_warm += 1
+    res = run_cpu_leg(wl, weights, ring, seconds=0, max_steps=steps, warmup=0, run=run)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(wl, args, ring_sets=2),
+        "steps": steps, "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(wl, args, batch_per_gpu=B),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -251,13 +273,15 @@ def reference_arm(args, wl, rank, world):
     emit(line)
 
 
-def config_dict(wl, args, ring_sets):
-    return {"workload": f"BASELINE configs[1]: {wl.name}", "image": [wl.height, wl.width], "batch_per_gpu": wl.batch,
+def config_dict(wl, args, batch_per_gpu=None):
+    """The workload description -- identical for both arms (the driver compares it)."""
+    return {"workload": f"BASELINE configs[{wl.config_id - 1}]: {wl.name}", "image": [wl.height, wl.width],
+            "batch_per_gpu": wl.batch if batch_per_gpu is None else batch_per_gpu,
             "anchors_per_location": wl.n_loc, "anchors_per_image": wl.num_anchors,
             "score_threshold": wl.score_threshold, "iou_threshold": wl.iou_threshold,
-            "max_detections": wl.max_detections, "prn": args.prn_mode, "parallelism": f"dp{args.gpus} (image-sharded, no collective)",
-            "l2": f"inputs rotate over {ring_sets} distinct batches (> 126 MB L2 in total), no flush",
-            "lanes": f"{max(1, getattr(args, 'lanes', 1))} Detector handle(s), one CUDA stream each, batches fed round-robin"}
+            "max_detections": wl.max_detections, "prn": args.prn_mode,
+            "parallelism": f"dp{args.gpus} (image-sharded, no collective)",
+            "l2": "inputs rotate over distinct batches whose total size exceeds the 126 MB L2, no flush"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU legs
@@ -275,14 +299,16 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from multiposenet_b200 import DetectorConfig, DetectorLanes
+    from multiposenet_b200 import DetectorConfig, DetectorLanes, parallel
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # the host-side result gather of the e2e leg (no device collective)
 
     def barrier():
         if world > 1:
@@ -290,22 +316,29 @@ def main():
         torch.cuda.synchronize()
 
     K, Wm = args.steps, max(args.warmup, 3)
+    B = batch_per_gpu(wl, args)
     weights = synthetic.make_prn_weights()
     n_lanes = max(1, args.lanes)
     lanes = DetectorLanes(weights, DetectorConfig(
-        max_batch=wl.batch, max_height=wl.height, max_width=wl.width, max_boxes=wl.max_detections,
+        max_batch=B, max_height=wl.height, max_width=wl.width, max_boxes=wl.max_detections,
         score_threshold=wl.score_threshold, iou_threshold=wl.iou_threshold, scale_multipliers=wl.multipliers,
         aspect_ratios=wl.ratios, prn_mode=args.prn_mode, prn_modes_allocated=(args.prn_mode,), device=local_rank),
         lanes=n_lanes)
     det = lanes.detectors[0]            # the single-lane, e2e and profiling legs run on this handle
 
-    probe = synthetic.make_inputs(wl, replicate=100 * rank)
+    # weak: rank r runs its own batches; strong: rank r runs images [r B, (r + 1) B) of the workload's batches
+    def make_set(r):
+        if args.scaling == "strong":
+            full = synthetic.make_inputs(wl, replicate=r)
+            return parallel.shard_inputs(full, rank, world)[0]
+        return synthetic.make_inputs(wl, replicate=100 * rank + r)
+
+    probe = make_set(0)
     n_sets = max(2, -(-int(1.3 * L2_BYTES) // set_bytes(probe)))
-    ring = [probe] + [synthetic.make_inputs(wl, replicate=100 * rank + r) for r in range(1, n_sets)]
+    ring = [probe] + [make_set(r) for r in range(1, n_sets)]
     names = ("encoded_boxes", "class_logits", "heatmap_logits")
-    dev_ring = [{k: torch.from_numpy(s[k]).to(dev) for k in names} for s in ring]
-    pin_ring = [{k: torch.from_numpy(s[k]).pin_memory() for k in names} for s in ring]
-    B = wl.batch
+    dev_ring = [{k: torch.from_numpy(np.ascontiguousarray(s[k])).to(dev) for k in names} for s in ring]
+    pin_ring = [{k: torch.from_numpy(np.ascontiguousarray(s[k])).pin_memory() for k in names} for s in ring]
 
     def dev_step(i):
         s = dev_ring[i % n_sets]
@@ -325,26 +358,43 @@ def main():
             ms = float(t.item())
         return ms
 
+    def timed_blocks(step, prologue=None, epilogue=None):
+        """EXACTLY K steps between two CUDA events on `side`, barrier + synchronize on both sides, max over ranks.  The
+        block is repeated until --min-seconds of device time have been measured (a 20-step block of this path lasts
+        1.6 ms); the median block is the reported one, the fastest is kept beside it."""
+        blocks, launches, first = [], 0, Wm
+        while True:
+            barrier()
+            launches0 = lanes.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            with torch.cuda.stream(side):
+                e0.record()
+                if prologue:
+                    prologue(e0)
+                for i in range(K):
+                    out = step(first + i)
+                if epilogue:
+                    epilogue()
+                e1.record()
+            barrier()
+            t1 = time.time()
+            if sampler:
+                sampler.mark(t0, t1)
+            launches = int(lanes.launch_count() - launches0)
+            blocks.append(max_over_ranks(e0.elapsed_time(e1)))
+            first += K
+            # every rank must take the same decision: the block times are already the max over ranks
+            if sum(blocks) >= 1e3 * args.min_seconds or len(blocks) >= 200:
+                break
+        return statistics.median(blocks), min(blocks), len(blocks), launches, out
+
     # (a) one handle, one stream: K calls back to back
     torch.cuda.synchronize()
     with torch.cuda.stream(side):
         for i in range(max(Wm, n_sets)):
             out = dev_step(i)
-    barrier()
-    launches0 = lanes.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    with torch.cuda.stream(side):
-        e0.record()
-        for i in range(K):
-            out = dev_step(Wm + i)
-        e1.record()
-    barrier()
-    t1 = time.time()
-    if sampler:
-        sampler.mark(t0, t1)
-    n_launches = int(lanes.launch_count() - launches0)
-    single_ms = max_over_ranks(e0.elapsed_time(e1))
+    single_ms, single_min_ms, single_blocks, n_launches, out = timed_blocks(dev_step)
     persons = int(out["person_offsets"][-1].item())
 
     # (b) the K steps fed round-robin to the lanes; the events sit on `side`, every lane starts after e0 and `side`
@@ -353,30 +403,14 @@ def main():
         s = dev_ring[i % n_sets]
         return lanes.submit(s["encoded_boxes"], s["class_logits"], s["heatmap_logits"], (wl.height, wl.width))
 
-    dev_ms = single_ms
+    dev_ms, dev_min_ms, dev_blocks = single_ms, single_min_ms, single_blocks
     if n_lanes > 1:
         with torch.cuda.stream(side):
             lanes.fork()
             for i in range(max(Wm, n_sets * n_lanes)):      # every lane sees every input set once (graph capture)
                 lane_step(i)
             lanes.join()
-        barrier()
-        launches0 = lanes.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        with torch.cuda.stream(side):
-            e0.record()
-            lanes.fork(e0)
-            for i in range(K):
-                lane_step(Wm + i)
-            lanes.join()
-            e1.record()
-        barrier()
-        t1 = time.time()
-        if sampler:
-            sampler.mark(t0, t1)
-        n_launches = int(lanes.launch_count() - launches0)
-        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        dev_ms, dev_min_ms, dev_blocks, n_launches, _ = timed_blocks(lane_step, prologue=lanes.fork, epilogue=lanes.join)
     if world > 1:
         t = torch.tensor([n_launches], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -384,8 +418,15 @@ def main():
 
     # ---- leg 2: end to end through host buffers --------------------------------------------------------------
     # every step copies its inputs from pinned host memory, runs the path and copies all seven outputs back; up to
-    # HOST_DEPTH steps are in flight so that the PCIe copies of neighbouring steps overlap the kernels.
+    # HOST_DEPTH steps are in flight so that the PCIe copies of neighbouring steps overlap the kernels.  At N > 1 every
+    # step's detections and keypoints are then gathered on rank 0 in rank order over the HOST (gloo: fixed-size blocks, no
+    # device collective -- north_star's "host-side result gather"); the heatmaps stay with the rank that produced them.
     from multiposenet_b200._lib import HOST_DEPTH
+
+    def consume(bufs):
+        _ = int(bufs["num_boxes"][0])                  # the step's result is read on the host
+        if world > 1:
+            parallel.gather_packed(bufs, dst=0, group=host_group)
 
     def host_loop(n, first, depth):
         pend = []
@@ -396,18 +437,18 @@ def main():
             if len(pend) >= depth:
                 t, bufs = pend.pop(0)
                 det.wait(t)
-                _ = int(bufs["num_boxes"][0])          # the step's result is read on the host
+                consume(bufs)
         while pend:
             t, bufs = pend.pop(0)
             det.wait(t)
-            _ = int(bufs["num_boxes"][0])
+            consume(bufs)
         return bufs
 
     host_loop(Wm, 0, HOST_DEPTH)
-    # Two passes of K steps each, the faster one is reported (both are in the line): the pinned copies share the host's
-    # memory system with whatever else runs on the machine, and one disturbed pass has been seen to cost 60 %.
+    # Passes of K steps each until --min-seconds (at least two); the MEDIAN pass is reported, all of them are in the line:
+    # the pinned copies share the host's memory system with whatever else runs on the machine.
     e2e_passes = []
-    for _ in range(2):
+    while len(e2e_passes) < 2 or (sum(e2e_passes) < args.min_seconds and len(e2e_passes) < 50):
         barrier()
         t0 = time.time()
         w0 = time.perf_counter()
@@ -422,7 +463,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             pass_s = float(t.item())
         e2e_passes.append(pass_s)
-    e2e_s = min(e2e_passes)
+    e2e_s = statistics.median(e2e_passes)
     del hout
     w0 = time.perf_counter()
     host_loop(min(K, 50), 0, 1)                        # one call at a time: the latency of a single step
@@ -433,7 +474,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- leg 3: per-kernel times (profiling events; not part of `value`) ---------------------------------------
-    roofline, kernels = None, None
+    roofline, kernels, stages = None, None, None
     if rank == 0:
         det.set_profiling(True)
         acc, order = {}, []
@@ -457,49 +498,62 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         kernels = {}
-        step_ms = sum(statistics.mean(v) for v in acc.values())
+        mean = {n: statistics.mean(acc[n]) for n in order}
+        step_ms = sum(mean.values())
         for name in order:
-            ms = statistics.mean(acc[name])
-            ab = algorithmic_bytes(name, wl, B, persons, n_cand, args.prn_mode)
-            kernels[name] = {"ms": round(ms, 5), "share": round(ms / step_ms, 4),
-                             "alg_bytes": ab, "gbs": None if not ab else round(ab / ms / 1e6, 1)}
+            ms = mean[name]
+            ab, mv = algorithmic_bytes(name, wl, B, persons, n_cand, args.prn_mode)
+            kernels[name] = {"ms": round(ms, 5), "share": round(ms / step_ms, 4), "alg_bytes": ab, "moved_bytes": mv,
+                             "gbs": None if not ab else round(ab / ms / 1e6, 1),
+                             "gbs_moved": None if not mv else round(mv / ms / 1e6, 1),
+                             "frac_of_hbm_peak": None if not mv else round(mv / ms / 1e6 / hbm_peak, 3)}
             if name in ("prn_big_fc1", "prn_big_fc2", "prn_bf16_fc1", "prn_bf16_fc2"):      # tensor-bound layers: 2 N D H flop
                 kernels[name]["tflops"] = round(2.0 * persons * D * HIDDEN / ms / 1e9, 1)
-        top = max([n for n in order if kernels[n]["alg_bytes"]], key=lambda n: statistics.mean(acc[n]))
-        ab = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
-        ach = ab / statistics.mean(acc[top]) / 1e6
+        # the heatmap stage as a whole (create_pb.py:73-76, 90-94): logits in once, the two outputs out once
+        hm = [n for n in ("logit_minmax", "heatmap_norm", "heatmap") if n in mean]
+        if hm:
+            t = sum(mean[n] for n in hm)
+            pix = (wl.height // 4) * (wl.width // 4)
+            stages = {"heatmap_stage": {"kernels": hm, "ms": round(t, 5), "alg_bytes": 144 * pix * B,
+                                        "gbs": round(144 * pix * B / t / 1e6, 1)}}
+        cands = [n for n in order if kernels[n]["alg_bytes"]]
+        top = max(cands, key=lambda n: mean[n])
+        ab, _ = algorithmic_bytes(top, wl, B, persons, n_cand, args.prn_mode)
         traffic = None
         if args.workload == "c2":          # the committed ncu capture was taken at this workload's sizes
             try:
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
             except Exception:
                 pass
-        launch_ms = statistics.mean(acc[top])
+        launch_ms = mean[top]
         timing = "CUDA events between direct launches (profiling pass)"
         if top == "prn_fused":
             # the dominant kernel alone: K replays of a graph that contains only this kernel (every other stage skipped,
             # its inputs -- the crops of the last full step -- stay in place), CUDA events on the launching stream
             # (the skipped stages are the only readers of the rotating inputs, so a few sets are enough: a workload with
             # a long input ring would otherwise spend this pass capturing one new graph per set)
-            det.debug_skip(1 | 2 | 4 | 8 | 32)
+            det.debug_skip(1 | 2 | 8 | 32)
             m_sets = min(n_sets, 7)
+            reps = max(min(K, 200), 100)
             with torch.cuda.stream(side):
                 for i in range(max(10, m_sets)):
                     dev_step(i % m_sets)
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record()
-                for i in range(min(K, 200)):
+                for i in range(reps):
                     dev_step(i % m_sets)
                 p1.record()
             torch.cuda.synchronize()
             det.debug_skip(0)
-            launch_ms = p0.elapsed_time(p1) / min(K, 200)
-            timing = "CUDA events around graph replays that contain only this kernel (all other stages skipped)"
+            launch_ms = p0.elapsed_time(p1) / reps
+            timing = f"CUDA events around {reps} graph replays that contain only this kernel (all other stages skipped)"
         ach = ab / launch_ms / 1e6
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": which,
-                    "alg_bytes_per_launch": ab, "avg_launch_ms": round(launch_ms, 5), "timing": timing,
-                    "avg_launch_ms_profiling_pass": round(statistics.mean(acc[top]), 5),
+                    "alg_bytes_per_launch": ab, "alg_bytes_formula": "SURVEY 8(d): PRN weights + biases once + persons x 274176 B "
+                    "(fp32 crops in, logits out)" if top == "prn_fused" else "DESIGN.md section 4",
+                    "avg_launch_ms": round(launch_ms, 5), "timing": timing,
+                    "avg_launch_ms_profiling_pass": round(mean[top], 5),
                     "persons_per_batch": persons, "candidates_per_batch": n_cand}
 
     # ---- leg 4: CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------
@@ -518,19 +572,24 @@ def main():
     line = {
         "metric": METRIC, "value": images / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": dev_ms / K, "lanes": n_lanes,
+        "timed_blocks": {"count": dev_blocks, "steps_per_block": K, "reported": "median block",
+                         "fastest_block_ms_per_step": dev_min_ms / K, "fastest_block_value": images / (dev_min_ms / 1e3)},
         "single_lane": {"value": images / (single_ms / 1e3), "unit": UNIT, "ms_per_step": single_ms / K,
+                        "fastest_block_ms_per_step": single_min_ms / K, "blocks": single_blocks,
                         "note": "the same K steps back to back on one handle and one stream"},
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32 (decode/NMS/crop/softmax) + " + ("bf16 tcgen05, f32 accumulate (PRN)" if args.prn_mode == "bf16" else "f32 (PRN)"),
-        "data": "synthetic", "config": config_dict(wl, args, n_sets),
+        "data": "synthetic", "config": config_dict(wl, args, batch_per_gpu=B), "input_ring_sets": n_sets,
         "e2e": {"value": images / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K, "passes_ms_per_step": [round(1e3 * x / K, 5) for x in e2e_passes],
-                "in_flight": HOST_DEPTH, "serial_ms_per_step": serial_ms,
+                "reported": "median pass", "in_flight": HOST_DEPTH, "serial_ms_per_step": serial_ms,
                 "input_bytes_per_step": in_bytes,
+                "result_gather": None if world == 1 else "every step: detections + keypoints of all ranks gathered on rank 0 "
+                                                         "over the host (gloo, fixed-size blocks)",
                 "note": "class logits and heatmap logits are copied by DMA; the box codes stay in pinned host memory "
                         "and only the rows of confident anchors are gathered over PCIe by the NMS kernel"},
         "gpu_launches": n_launches,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "stages": stages,
     }
     emit(line)
 

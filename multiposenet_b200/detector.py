@@ -528,8 +528,8 @@ class Detector:
         return np.frombuffer(buf, dtype=np.uint64, count=g.value * 16).reshape(g.value, 16).copy()
 
     def debug_skip(self, mask):
-        """Development aid (mpn_debug_skip): do not launch the stages whose bit is set (1 detect, 2 heatmap, 4 normalise,
-        8 crop, 16 PRN, 32 keypoint decode); their outputs keep the previous call's values."""
+        """Development aid (mpn_debug_skip): do not launch the stages whose bit is set (1 detect, 2 heatmap stage, 8 crop,
+        16 PRN, 32 keypoint decode); their outputs keep the previous call's values."""
         self._check(self._lib.mpn_debug_skip(self._handle, int(mask)))
 
     def launch_count(self):

@@ -57,3 +57,38 @@ def gather_results(result, dst=0, group=None):
     if rank != dst:
         return None
     return merge_results(bucket)
+
+
+_PACKED = ("boxes", "scores", "num_boxes", "keypoint_scores", "keypoint_positions")
+
+
+def gather_packed(result, dst=0, group=None, merge=True):
+    """The same gather for a stream of steps: every rank's detections and keypoints (the padded, fixed-size buffers of one
+    Detector call: boxes [B, max_det, 4], scores [B, max_det], num_boxes [B], keypoint_scores / keypoint_positions
+    [B * max_det, ...]) travel as ONE fixed-size block per rank in one host-side `gather` (gloo) -- no pickling, no device
+    collective.  `result` holds torch CPU tensors or numpy arrays; returns the merged dict (create_pb.py:53-61 layout, persons
+    of all ranks concatenated in rank order) on `dst`, None elsewhere."""
+    import torch
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    parts = [torch.as_tensor(result[k]) for k in _PACKED]
+    flat = torch.cat([p.reshape(-1).view(torch.float32) for p in parts])      # num_boxes: int32 bits carried as float32
+    bucket = [torch.empty_like(flat) for _ in range(world)] if rank == dst else None
+    dist.gather(flat, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    if not merge:
+        return bucket
+    per_rank = []
+    for blk in bucket:
+        r, o = {}, 0
+        for k, p in zip(_PACKED, parts):
+            n = p.numel()
+            a = blk[o:o + n].view(p.dtype).reshape(p.shape).numpy()
+            o += n
+            r[k] = a
+        n_persons = int(r["num_boxes"].sum())
+        r["keypoint_scores"] = r["keypoint_scores"][:n_persons]
+        r["keypoint_positions"] = r["keypoint_positions"][:n_persons]
+        per_rank.append(r)
+    return merge_results(per_rank)

@@ -97,6 +97,20 @@ def _worker(rank, world, port, n_images, out_path):
         lo, hi = parallel.shard_range(n_images, rank, world)
         res = _fake_result(lo, hi)
         merged = parallel.gather_results(res, dst=0)
+        # the fixed-size gather of the bench's e2e leg: padded per-call buffers (persons padded to B * max_det rows)
+        lo0, hi0 = parallel.shard_range(8, rank, world)               # equal shards: every rank's block has the same size
+        pad = _fake_result(lo0, hi0)
+        n = int(pad["num_boxes"].sum())
+        rows = (hi0 - lo0) * 5
+        pad["keypoint_scores"] = np.concatenate([pad["keypoint_scores"], np.full((rows - n, 17), -1, np.float32)])
+        pad["keypoint_positions"] = np.concatenate([pad["keypoint_positions"], np.full((rows - n, 17, 2), -1, np.float32)])
+        packed = parallel.gather_packed({k: torch.from_numpy(v) for k, v in pad.items()}, dst=0)
+        if rank == 0:
+            want = parallel.merge_results([_fake_result(*parallel.shard_range(8, r, world)) for r in range(world)])
+            for k in want:
+                assert np.array_equal(packed[k], want[k]), k
+        else:
+            assert packed is None
         # the bench's timing reduction: max over ranks
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -137,10 +151,21 @@ def test_bench_and_tools_compile_and_bench_formulas_hold():
     import bench
     wl = synthetic.WORKLOADS["c2"]
     D, Hd = 56 * 36 * 17, 1024
-    assert bench.algorithmic_bytes("prn_fused", wl, 8, 77, 1825, "bf16") == 2 * D * Hd * 2 + 77 * D * 10
-    assert bench.algorithmic_bytes("prn_fused", wl, 32, 2805, 66877, "bf16") is None      # idle above 256 persons
-    assert bench.algorithmic_bytes("heatmap", wl, 8, 77, 1825, "bf16") == 2 * 72 * 160 * 160 * 8
-    assert bench.algorithmic_bytes("keypoint_decode", wl, 8, 77, 1825, "bf16") == 77 * D * 4
+    # (compulsory per SURVEY 8(d), moved by the kernel as built)
+    w = 2 * D * Hd * 2 + (Hd + D) * 4
+    assert w == 140378112 + 141184
+    assert bench.algorithmic_bytes("prn_fused", wl, 8, 77, 1825, "bf16") == (w + 77 * 274176, w + 77 * D * 10)
+    assert bench.algorithmic_bytes("prn_fused", wl, 32, 2805, 66877, "bf16") == (None, None)      # idle above 256 persons
+    assert bench.algorithmic_bytes("heatmap", wl, 8, 77, 1825, "bf16")[0] == 2 * 72 * 160 * 160 * 8
+    assert bench.algorithmic_bytes("heatmap_norm", wl, 8, 77, 1825, "bf16") == (144 * 25600 * 8, 224 * 25600 * 8)
+    assert bench.algorithmic_bytes("logit_minmax", wl, 8, 77, 1825, "bf16") == (None, 72 * 25600 * 8)
+    assert bench.algorithmic_bytes("keypoint_decode", wl, 8, 77, 1825, "bf16")[0] == 77 * D * 4
+    # both arms describe the workload identically (the driver compares `config`), labelled from the workload itself
+    import argparse
+    a = argparse.Namespace(prn_mode="bf16", gpus=1, scaling="weak", lanes=3)
+    assert bench.config_dict(wl, a) == bench.config_dict(wl, argparse.Namespace(prn_mode="bf16", gpus=1, scaling="weak"))
+    assert bench.config_dict(synthetic.WORKLOADS["c4"], a)["workload"].startswith("BASELINE configs[3]")
+    assert bench.batch_per_gpu(synthetic.WORKLOADS["c4"], argparse.Namespace(scaling="strong", gpus=8)) == 8
 
 
 @pytest.mark.timeout(600)

@@ -28,7 +28,7 @@ def step_us(mask, K=300):
     return e0.elapsed_time(e1) * 1e3 / K
 full = step_us(0)
 print(f"full step {full:7.1f} us")
-for name, bit in (("detect branch", 1), ("heatmap", 2), ("normalise", 4), ("heatmap+normalise", 6), ("crop", 8), ("prn", 16),
+for name, bit in (("detect branch", 1), ("heatmap stage", 2), ("crop", 8), ("prn", 16),
                   ("decode", 32), ("all but prn", 47), ("all but front", 56), ("nothing launched", 63)):
     t = step_us(bit)
     print(f"without {name:18s} {t:7.1f} us   (saves {full - t:6.1f})")

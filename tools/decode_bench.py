@@ -1,5 +1,4 @@
-"""Development aid: keypoint decode kernel alone.  python tools/decode_bench.py [N ...]
-(MPN_TUNE_DECODE=0 forces the register kernel, =1 the streaming kernel)"""
+"""Development aid: keypoint decode kernel alone.  python tools/decode_bench.py [N ...]"""
 import os, sys
 import numpy as np
 import torch
@@ -21,5 +20,5 @@ for n in ns:
         det.keypoint_decode(x)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / K
-    print(f"N={n:6d}  {us:8.1f} us per call  {n * 56 * 36 * 17 * 4 / us / 1e6:7.2f} TB/s  (mode {os.environ.get('MPN_TUNE_DECODE', 'auto')})")
+    print(f"N={n:6d}  {us:8.1f} us per call  {n * 56 * 36 * 17 * 4 / us / 1e6:7.2f} TB/s")
 det.close()
