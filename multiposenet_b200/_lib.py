@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpn_b200.so")
+# MPN_LIB: a variant build of the same ABI (multiposenet_b200/build.py: VARIANTS) for measurements; default: the product library
+LIB_PATH = os.environ.get("MPN_LIB") or os.path.join(HERE, "libmpn_b200.so")
 
 MPN_MAX_LEVELS = 8
 MPN_MAX_ANCHOR_SHAPES = 16

@@ -42,6 +42,24 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# Variant builds for measurements (never loaded unless MPN_LIB points at them): name -> extra nvcc flags
+VARIANTS = {"eighths": ["-DMPN_FC1_EIGHTHS=1"]}
+
+
+def build_variant(name, force=False):
+    """libmpn_b200_<name>.so next to the product library, compiled with VARIANTS[name]."""
+    global OBJ, LIB
+    keep = (OBJ, LIB, list(NVCC_FLAGS))
+    try:
+        OBJ = os.path.join(HERE, "_obj_" + name)
+        LIB = os.path.join(HERE, f"libmpn_b200_{name}.so")
+        NVCC_FLAGS.extend(VARIANTS[name])
+        return build_library(force=force)
+    finally:
+        OBJ, LIB = keep[0], keep[1]
+        NVCC_FLAGS[:] = keep[2]
+
+
 def build_library(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
@@ -85,4 +103,6 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    for v in [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]:
+        print(build_variant(v, force="--force" in sys.argv))
     print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

@@ -45,8 +45,15 @@ namespace {
 
 using namespace tc;
 
+#ifdef MPN_FC1_EIGHTHS
+// Variant build (tools/variants.py): fc1 on hidden EIGHTHS x 18 K splits instead of quarters x 37 -- half the partial sums
+// (6 MB out and back at 78 persons), twice the activation re-reads, 16 KB weight boxes, 4 idle CTAs in fc1.
+constexpr int kHq = 8;
+constexpr int kFc1N = 128, kFc2N = 240;
+#else
 constexpr int kHq = 4;                                   // hidden quarters of fc1
-constexpr int kFc1N = 256, kFc2N = 240;                  // UMMA N of the two layers
+constexpr int kFc1N = 256, kFc2N = 240;                  // weight rows per CTA tile of the two layers
+#endif
 constexpr int kXBox = 16;                                // rows per activation TMA box (persons are padded to 16)
 constexpr int kXBoxBytes = kXBox * 128;
 constexpr int kXTileBytes = 128 * 128;                   // one 128-row activation tile (16 KB)
@@ -302,7 +309,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t w_addr = smem_u32(smem + st * kWTileBytes);
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + x_base + st * x_stride));
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
+                    for (int m = 0; m < kFc1N / 128; ++m) {
                         const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
@@ -359,7 +366,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
             if (tid_e == 0) stamp(args, 3);                                 // fc1 accumulators complete
-            for (int item = cg; item < n_items; item += 4) {
+            for (int item = cg; item < (kFc1N / 128) * nb; item += 4) {
                 const int m = item >= nb ? 1 : 0, ch = item - m * nb;
                 uint32_t r[16];
                 tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
