@@ -13,28 +13,35 @@ def test_evaluator_reproduces_reference_metrics_golden():
     g = np.load(os.path.join(HERE, "golden", "metrics.npz"))
     assert int(g["n"]) >= 6
     for k in range(int(g["n"])):
-        ev = metrics.Evaluator()
+        ev = metrics.DetectionEvaluator()
         for i in range(int(g[f"n_images_{k}"])):
-            ev.add_groundtruth(str(i), g[f"gt_{k}_{i}"])
-            ev.add_detections(str(i), g[f"det_{k}_{i}"], g[f"score_{k}_{i}"])
+            ev.add_image(g[f"gt_{k}_{i}"], g[f"det_{k}_{i}"], g[f"score_{k}_{i}"])
         m = ev.evaluate(0.5)
         got = np.array([float(m[name]) for name in metrics.METRIC_NAMES], np.float64)
         assert np.array_equal(got, g[f"metrics_{k}"]), (k, got, g[f"metrics_{k}"])
 
 
 def test_metric_known_answers():
-    ev = metrics.Evaluator()
+    ev = metrics.DetectionEvaluator()
     gt = np.array([[0.1, 0.1, 0.5, 0.5], [0.6, 0.6, 0.9, 0.9]], np.float32)
     ev.add_image(gt, gt.copy(), np.array([0.9, 0.8], np.float32))                 # perfect detector
     m = ev.evaluate()
     assert m["AP"] == 1.0 and m["total_FP"] == 0 and m["total_FN"] == 0 and abs(m["mean_iou_for_TP"] - 1.0) < 1e-6
-    ev.initialize()
+    ev.reset()
     ev.add_image(gt, np.array([[0.1, 0.1, 0.5, 0.5], [0.1, 0.1, 0.5, 0.5]], np.float32), np.array([0.9, 0.8], np.float32))
     m = ev.evaluate()                                                            # the duplicate is a false positive
     assert m["total_FP"] == 1 and m["total_FN"] == 1 and m["AP"] == 0.5
-    assert metrics.Evaluator().evaluate()["AP"] == 0.0                          # nothing at all (metrics.py:140, :199-200)
+    assert metrics.DetectionEvaluator().evaluate()["AP"] == 0.0                 # nothing at all (metrics.py:140, :199-200)
+    # a detection whose best box is already claimed is a false positive even if it overlaps a second box well enough
+    two = np.array([[0.0, 0.0, 0.5, 0.5], [0.0, 0.1, 0.5, 0.6]], np.float32)
+    ev.reset()
+    ev.add_image(two, np.array([[0.0, 0.0, 0.5, 0.5], [0.0, 0.04, 0.5, 0.54]], np.float32), np.array([0.9, 0.8], np.float32))
+    m = ev.evaluate()
+    assert m["total_FP"] == 1 and m["total_FN"] == 1
+    iou = metrics.pairwise_iou(two, two)
+    assert iou[0, 0] == 1.0 and abs(iou[0, 1] - 0.4 / 0.6) < 1e-6 and metrics.pairwise_iou(two[:0], two).shape == (0, 2)
     # num_boxes cuts the padded rows (metrics.py:45-50)
-    ev.initialize()
+    ev.reset()
     ev.add_batch([gt], {"boxes": np.concatenate([gt, np.zeros((3, 4), np.float32)])[None],
                         "scores": np.array([[0.9, 0.8, 0, 0, 0]], np.float32), "num_boxes": np.array([2])})
     assert ev.evaluate()["total_FP"] == 0
