@@ -340,6 +340,7 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     MPN_ALLOC(h->minmax_ws, B * 17 * 2);
     h->hm_partial_chunks = (h->max_hm_pix / 64 + 1) / 2 + 1;      // per image; every heatmap launcher stays within it
     MPN_ALLOC(h->hm_partial, B * (size_t)h->hm_partial_chunks * 17 * 2);
+    MPN_ALLOC(h->hm_partial2, B * (size_t)h->hm_partial_chunks * 17 * 2);
     MPN_ALLOC(h->hm_counter, B);
     cudaMemset(h->hm_counter, 0, B * sizeof(unsigned int));
     cudaMemset(h->nh_ws, 0, B * h->max_hm_pix * 20 * sizeof(float));     // pad channels 17..19 stay zero for good
@@ -434,7 +435,7 @@ void mpn_destroy(mpn_handle *h)
     prn_fused_release(h);
     prn_big_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
-                    h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_counter, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
+                    h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_partial2, h->hm_counter, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -548,12 +549,13 @@ int mpn_heatmaps_normalised(mpn_handle *h, const float *heatmap_logits, int32_t 
         return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits / normalised must be 16-byte aligned");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = launched(h, launch_logit_minmax(heatmap_logits, batch, hm_height, hm_width, h->minmax_ws, h->hm_partial,
-                                             h->hm_partial_chunks, h->hm_counter, h->waves.minmax, s), true, "logit min/max");
+    int n_chunks = 0;
+    int rc = launched(h, launch_logit_minmax(heatmap_logits, batch, hm_height, hm_width, h->hm_partial2, h->hm_partial_chunks,
+                                             h->waves.minmax, &n_chunks, s), true, "logit min/max");
     if (rc) return rc;
     return launched(h, launch_heatmap_norm(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
-                                           h->minmax_ws, normalised ? normalised : h->nh_ws, minmax, h->waves.norm, s), false,
-                    "heatmaps + normalise");
+                                           h->hm_partial2, n_chunks, h->minmax_ws, normalised ? normalised : h->nh_ws, minmax,
+                                           h->waves.norm, s), false, "heatmaps + normalise");
 }
 
 int mpn_crop_padded(mpn_handle *h, const float *normalised, int32_t batch, int32_t hm_height, int32_t hm_width,
@@ -692,9 +694,10 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     float *kh = out->keypoint_heatmaps ? out->keypoint_heatmaps : h->kh_ws;
     // 1a. padded path, pass 1 of the heatmap stage: min / max of the logits (create_pb.py:90,92 through the monotone
     //     sigmoid).  A short HBM stream with no dependency on anything: it runs BESIDE the candidate scan.
+    int n_chunks = 0;
     if (padded && !(skip & 2u))
-        rc = launched(h, launch_logit_minmax(in->heatmap_logits, in->batch, hh, ww, h->minmax_ws, h->hm_partial,
-                                             h->hm_partial_chunks, h->hm_counter, h->waves.minmax, sa), true, "logit min/max");
+        rc = launched(h, launch_logit_minmax(in->heatmap_logits, in->batch, hh, ww, h->hm_partial2, h->hm_partial_chunks,
+                                             h->waves.minmax, &n_chunks, sa), true, "logit min/max");
     if (rc) return rc;
     // 1. scores, threshold, decode, NMS, person list        (retinanet.py:56-81, nms.py:6-61, create_pb.py:96-103)
     // The big heatmap grid (thousands of CTAs) is released only once the candidate scan has finished, i.e. at the moment
@@ -714,7 +717,8 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     //    activations and their min / max only (one pass).
     if (!(skip & 2u))
         rc = padded ? launched(h, launch_heatmap_norm(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks,
-                                                      h->minmax_ws, h->nh_ws, nullptr, h->waves.norm, sa), false, "heatmaps + normalise")
+                                                      h->hm_partial2, n_chunks, h->minmax_ws, h->nh_ws, nullptr, h->waves.norm,
+                                                      sa), false, "heatmaps + normalise")
                     : launched(h, launch_heatmaps(in->heatmap_logits, in->batch, hh, ww, kh, out->segmentation_masks,
                                                   h->minmax_ws, nullptr, h->hm_partial, h->hm_counter, h->waves.one_pass, sa), false, "heatmaps");
     if (rc) return rc;

@@ -120,10 +120,10 @@ int launch_heatmap_head(const float *x, const float *w, const float *bias, int B
                         float *seg, float *minmax_ws, float *minmax_out, int *partial_ws, unsigned int *counter_ws,
                         cudaStream_t s);
 // the two-pass form (padded crop path): min / max from the logits, then activation + normalisation in one pass
-int launch_logit_minmax(const float *hml, int B, int hh, int ww, float *minmax_ws, int *partial_ws, int partial_chunks_cap,
-                        unsigned int *counter_ws, int slots, cudaStream_t s);
-int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const float *minmax_ws, float *nh,
-                        float *minmax_out, int slots, cudaStream_t s);
+int launch_logit_minmax(const float *hml, int B, int hh, int ww, int *partial_ws, int partial_chunks_cap, int slots,
+                        int *n_chunks, cudaStream_t s);
+int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const int *partial_ws, int n_chunks,
+                        float *minmax_ws, float *nh, float *minmax_out, int slots, cudaStream_t s);
 // crop of the padded (20 floats / pixel) normalised map written by launch_heatmap_norm
 bool crop_padded_supported(int crop_h, int crop_w);
 int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,

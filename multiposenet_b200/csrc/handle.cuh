@@ -60,7 +60,9 @@ struct mpn_handle {
     float *nh_ws;           // normalised heatmaps (create_pb.py:93-94), never returned
     float *minmax_ws;
     int *hm_partial;        // [B, chunks, 17, 2] per-CTA (min, max) of the heatmap kernels
-    int hm_partial_chunks;  // chunks per image the array holds
+    int *hm_partial2;       // the same for the logit min / max pass of the two-pass form (ordered keys): a buffer of its own,
+                            // because that pass has no dependency on the previous call's kernels of the other branch
+    int hm_partial_chunks;  // chunks per image either array holds
     mpn::HeatmapWaves waves;
     unsigned int *hm_counter;   // [B] CTAs finished per image (self re-arming)
     // PRN workspace / weights

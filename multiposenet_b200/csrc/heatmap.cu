@@ -7,12 +7,11 @@
 //   create_pb.py:106-109  tf.image.crop_and_resize(heatmaps, boxes, box_ind, crop_size=[56, 36])  (bilinear, extrapolation 0)
 //   inference/utils.py:29-52  get_keypoints
 //
-// heatmap_kernel is a pure HBM stream: 72 B in, 72 B out per pixel.  The [.., 18] input is read as a flat float4
-// stream; a CTA of 288 threads covers 64 pixels per step, so thread t always sees the same four channels
-// ((4t + j) mod 18) and keeps its running min / max in registers.  The 17-channel and 1-channel outputs are
-// re-packed through shared memory so that both are written as aligned float4 as well.
-// The normalised heatmap is never written: crop_kernel normalises each bilinear tap on the fly (same arithmetic,
-// same order, as normalising the whole map first).
+// The heatmap kernels are HBM streams over 64-pixel tiles (64 x 18 = 1152 consecutive floats of the NHWC logits) by CTAs
+// of 288 threads.  Thread t owns elements t, t + 288, t + 576, t + 864 of a tile: 288 = 16 x 18, so ALL of them belong to
+// channel t mod 18 (pixels t / 18 + 16 k) -- one channel per thread, its running min / max or its normalisation constants
+// in a handful of registers -- and a warp's 32 lanes touch 32 consecutive floats in every load and every store (one
+// wavefront each; an earlier float4-per-thread map made every scalar store a stride-4 access of four wavefronts).
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -60,28 +59,11 @@ __device__ __forceinline__ void publish_minmax(int *s_min, int *s_max, int *s_la
     if (tid == 0) counter[img] = 0u;
 }
 
-// fold_minmax: every thread's four running (min, max) -> the CTA's, then publish.
-__device__ __forceinline__ void fold_minmax(const int (&ch)[4], const float (&mn)[4], const float (&mx)[4], int *s_min,
-                                            int *s_max, int *s_last, int *__restrict__ partial,
-                                            unsigned int *__restrict__ counter, int *__restrict__ minmax)
-{
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (ch[j] < kNK) {
-            atomicMin(&s_min[ch[j]], __float_as_int(mn[j]));     // sigmoid output is >= 0: integer order == float order
-            atomicMax(&s_max[ch[j]], __float_as_int(mx[j]));
-        }
-    }
-    __syncthreads();
-    publish_minmax(s_min, s_max, s_last, partial, counter, minmax);
-}
+constexpr int kPerThread = kHmPix * kCH / kHmThreads;      // 4 elements of a tile per thread
 
-// grid = (chunks per image, B).  Thread t of a CTA always sees the four channels (4 t + j) mod 18 of its 64-pixel tiles,
-// so its running min / max live in registers.  Outputs are written straight from registers: within a warp the 17-channel
-// rows are one contiguous run of addresses, so the scalar stores coalesce into full lines without a shared-memory
-// repack or any barrier in the streaming loop.  Per-CTA (min, max) go to a small partial array; the last CTA of each
-// image (threadfence + counter) folds them into minmax[b] and re-arms the counter, so no reset kernel is needed.
+// One pass (maps that take the per-tap crop path): activation, split, per-(image, channel) min / max.  grid = (chunks per
+// image, B).  Outputs are written straight from registers; per-CTA (min, max) go to a small partial array; the last CTA of
+// each image (threadfence + counter) folds them into minmax[b] and re-arms the counter, so no reset kernel is needed.
 __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__restrict__ hml, const int npix,
                                                              const int tiles_per_img, float *__restrict__ kh,
                                                              float *__restrict__ seg, int *__restrict__ partial,
@@ -92,49 +74,55 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
     __shared__ int s_last;
     const int img = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
-    // Straight-line inner code: every element gets the sigmoid (1 in 18 is the mask channel and keeps its raw value by a
-    // select), every element has ONE precomputed destination (its keypoint_heatmaps slot, or its segmentation_masks slot),
-    // and the mask channel's min / max registers are simply never merged.  No divergence inside a warp.
-    int ch[4];
-    bool is_kp[4];
-    float *dst[4];                         // destination of element j in tile 0 of this image
-    int dst_step[4];                       // ... and its stride from one tile to the next
-    float *kh_img = kh + (size_t)img * npix * kNK;
-    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int e = 4 * tid + j, p = e / kCH;
-        ch[j] = e - p * kCH;
-        is_kp[j] = ch[j] < kNK;
-        dst[j] = is_kp[j] ? kh_img + p * kNK + ch[j] : (seg_img ? seg_img + p : nullptr);
-        dst_step[j] = is_kp[j] ? kHmPix * kNK : kHmPix;
-    }
-    float mn[4], mx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { mn[j] = __int_as_float(0x7f800000); mx[j] = 0.0f; }
+    const int c = tid % kCH, p0 = tid / kCH;
+    const bool is_kp = c < kNK;
+    float mn = __int_as_float(0x7f800000), mx = 0.0f;
     if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
-
-    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
+    // Running pointers (tile blockIdx.x and tile blockIdx.x + gridDim.x, advanced by two grid strides per trip): every
+    // load and store of the loop is base + immediate.  A keypoint thread writes keypoint_heatmaps, a mask-channel
+    // thread segmentation_masks -- one output pointer pair per thread, the role fixed for the thread's life.
+    const size_t g = gridDim.x;
+    const float *sa = hml + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix) * kCH + tid, *sb = sa + g * (kHmPix * kCH);
+    float *oa = is_kp ? kh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kNK + c
+                      : (seg ? seg + (size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0 : nullptr);
+    const size_t ostep = is_kp ? kHmPix * kNK : kHmPix;
+    float *ob = oa ? oa + g * ostep : nullptr;
     // npix is a multiple of 64 on this path (images are multiples of 128): every tile is full.  Two tiles per trip.
     for (int tile = blockIdx.x; tile < tiles_per_img; tile += 2 * gridDim.x) {
-        const int tile2 = tile + gridDim.x;
-        const bool two = tile2 < tiles_per_img;
-        const float4 qa = __ldcs(src + (size_t)tile * kHmThreads + tid);
-        const float4 qb = two ? __ldcs(src + (size_t)tile2 * kHmThreads + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
+        const bool two = tile + (int)gridDim.x < tiles_per_img;
+        if (!two) sb = sa;                                   // no second tile: the first one again (min / max unchanged)
+        float va[kPerThread], vb[kPerThread];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float sa, sb;
-            exact_sigmoidf_pair(va[j], vb[j], sa, sb);      // two tiles' values share the packed FFMA2 / FMUL2 stream
-            mn[j] = fminf(mn[j], sa); mx[j] = fmaxf(mx[j], sa);
-            if (two) { mn[j] = fminf(mn[j], sb); mx[j] = fmaxf(mx[j], sb); }
-            if (dst[j]) {
-                dst[j][(size_t)tile * dst_step[j]] = is_kp[j] ? sa : va[j];
-                if (two) dst[j][(size_t)tile2 * dst_step[j]] = is_kp[j] ? sb : vb[j];
+        for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
+        float ya[kPerThread], yb[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            exact_sigmoidf_pair(va[k], vb[k], ya[k], yb[k]);      // two tiles' values share the packed FFMA2 / FMUL2 stream
+            mn = fminf(mn, fminf(ya[k], yb[k])); mx = fmaxf(mx, fmaxf(ya[k], yb[k]));
+        }
+        if (is_kp) {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                oa[k * (16 * kNK)] = ya[k];
+                if (two) ob[k * (16 * kNK)] = yb[k];
+            }
+        } else if (oa) {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                oa[k * 16] = va[k];
+                if (two) ob[k * 16] = vb[k];
             }
         }
+        sa += 2 * g * (kHmPix * kCH); sb += 2 * g * (kHmPix * kCH);
+        if (oa) { oa += 2 * g * ostep; ob += 2 * g * ostep; }
     }
-    fold_minmax(ch, mn, mx, s_min, s_max, &s_last, partial, counter, minmax);
+    __syncthreads();
+    if (is_kp) {
+        atomicMin(&s_min[c], __float_as_int(mn));            // sigmoid output is >= 0: integer order == float order
+        atomicMax(&s_max[c], __float_as_int(mx));
+    }
+    __syncthreads();
+    publish_minmax(s_min, s_max, &s_last, partial, counter, minmax);
 }
 
 // SURVEY section 8(f) row 2 -- the tail of KeypointSubnet fused in front of the activation pass:
@@ -278,245 +266,265 @@ __device__ __forceinline__ float key_float(unsigned k) { return __uint_as_float(
 constexpr unsigned kKeyPosInf = 0xff800000u;       // float_key(+inf)
 constexpr unsigned kKeyNegInf = 0x007fffffu;       // float_key(-inf)
 
+// Pass 1: per-CTA (min, max) of the logits of every channel, as ordered keys, to partial[img][chunk][17][2].  No fold
+// across CTAs here (no fence, no counter, no last-CTA tail on the critical path): pass 2 folds the chunks of its image.
 __global__ void __launch_bounds__(kHmThreads) logit_minmax_kernel(const float *__restrict__ hml, const int npix,
-                                                                  const int tiles_per_img, unsigned *__restrict__ partial,
-                                                                  unsigned int *__restrict__ counter,
-                                                                  float *__restrict__ minmax)
+                                                                  const int tiles_per_img, unsigned *__restrict__ partial)
 {
     __shared__ unsigned s_min[kNK], s_max[kNK];
-    __shared__ int s_last;
     const int img = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
-    int ch[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ch[j] = (4 * tid + j) % kCH;
-    float mn[4], mx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { mn[j] = __int_as_float(0x7f800000); mx[j] = -__int_as_float(0x7f800000); }
+    const int c = tid % kCH;
+    float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
     if (tid < kNK) { s_min[tid] = kKeyPosInf; s_max[tid] = kKeyNegInf; }
-    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
-    // four tiles per trip: four independent 16-byte loads in flight per thread (default caching: pass 2 re-reads the
-    // logits, from L2 whenever the call's maps fit)
+    const float *src = hml + (size_t)img * npix * kCH + tid;
+    // four tiles per trip: sixteen independent loads in flight per thread (default caching: pass 2 re-reads the logits,
+    // from L2 whenever the call's maps fit)
     for (int tile = blockIdx.x; tile < tiles_per_img; tile += 4 * gridDim.x) {
-        float4 q[4];
+        float v[4][kPerThread];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int t = tile + u * gridDim.x;          // past the end: the trip's first tile again (min / max unchanged)
-            q[u] = __ldg(src + (size_t)(t < tiles_per_img ? t : tile) * kHmThreads + tid);
+            const int t = tile + u * gridDim.x;              // past the end: the trip's first tile again (min / max unchanged)
+            const float *st = src + (size_t)(t < tiles_per_img ? t : tile) * (kHmPix * kCH);
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) v[u][k] = __ldg(st + k * kHmThreads);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { mn[j] = fminf(mn[j], v[j]); mx[j] = fmaxf(mx[j], v[j]); }
-        }
+            for (int k = 0; k < kPerThread; ++k) { mn = fminf(mn, v[u][k]); mx = fmaxf(mx, v[u][k]); }
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (ch[j] < kNK) {
-            atomicMin(&s_min[ch[j]], float_key(mn[j]));
-            atomicMax(&s_max[ch[j]], float_key(mx[j]));
-        }
+    if (c < kNK) {
+        atomicMin(&s_min[c], float_key(mn));
+        atomicMax(&s_max[c], float_key(mx));
     }
     __syncthreads();
     unsigned *my = partial + ((size_t)img * gridDim.x + blockIdx.x) * kNK * 2;
     if (tid < kNK) { my[tid * 2] = s_min[tid]; my[tid * 2 + 1] = s_max[tid]; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(counter + img, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+}
+
+// Pass 2.  Every CTA first folds the `n_chunks` per-CTA extremes pass 1 left for its image (a few KB from L2) and turns
+// them into its channel's constants with the monotone recipe: m = sigmoid(min logit), M = sigmoid(max logit)
+// (create_pb.py:90,92), d = M - m, 1 / d, mask = float(M > 0.2) (:91).  The first trip's logits are requested before the
+// wait on pass 1 (they do not depend on it).  CTA 0 of every image also publishes (m, M) to minmax[img].
+__global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float *__restrict__ hml, const int npix,
+                                                                     const int tiles_per_img, float *__restrict__ kh,
+                                                                     float *__restrict__ seg,
+                                                                     const unsigned *__restrict__ partial,
+                                                                     const int n_chunks, float *__restrict__ minmax,
+                                                                     float *__restrict__ nh)
+{
+    __shared__ unsigned s_min[kNK], s_max[kNK];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    const int c = tid % kCH, p0 = tid / kCH;
+    const bool is_kp = c < kNK;
     if (tid < kNK) { s_min[tid] = kKeyPosInf; s_max[tid] = kKeyNegInf; }
+    // running pointers, as in heatmap_kernel; a keypoint thread also owns a slot of the padded normalised map
+    const size_t g = gridDim.x;
+    const float *sa = hml + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix) * kCH + tid, *sb = sa + g * (kHmPix * kCH);
+    float *oa = is_kp ? kh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kNK + c
+                      : (seg ? seg + (size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0 : nullptr);
+    const size_t ostep = is_kp ? kHmPix * kNK : kHmPix;
+    float *ob = oa ? oa + g * ostep : nullptr;
+    float *na = nh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kPadCh + c, *nb = na + g * (kHmPix * kPadCh);
+    int tile = blockIdx.x;
+    float va[kPerThread], vb[kPerThread];
+    {
+        if (!(tile + (int)gridDim.x < tiles_per_img)) sb = sa;
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
+    }
     __syncthreads();
-    if (tid < kNK * 8) {
-        const int c = tid % kNK, slice = tid / kNK;
+    pdl_wait();                                        // pass 1 has completed
+    if (is_kp) {
         unsigned lo = kKeyPosInf, hi = kKeyNegInf;
-        for (int i = slice; i < (int)gridDim.x; i += 8) {
-            const unsigned *q = partial + ((size_t)img * gridDim.x + i) * kNK * 2 + c * 2;
-            lo = min(lo, __ldcg(q)); hi = max(hi, __ldcg(q + 1));
+        const unsigned *q = partial + (size_t)img * n_chunks * (kNK * 2) + c * 2;
+        for (int i = p0; i < n_chunks; i += kHmThreads / kCH) {
+            const uint2 e = __ldcg(reinterpret_cast<const uint2 *>(q + (size_t)i * (kNK * 2)));
+            lo = min(lo, e.x); hi = max(hi, e.y);
         }
         atomicMin(&s_min[c], lo); atomicMax(&s_max[c], hi);
     }
     __syncthreads();
-    if (tid < kNK) {
-        // the monotone recipe: activations of the extreme logits ARE the extreme activations (create_pb.py:90,92)
-        minmax[((size_t)img * kNK + tid) * 2] = exact_sigmoidf(key_float(s_min[tid]));
-        minmax[((size_t)img * kNK + tid) * 2 + 1] = exact_sigmoidf(key_float(s_max[tid]));
-    }
-    if (tid == 0) counter[img] = 0u;
-}
-
-// Pass 2.  Same element-to-thread map as heatmap_kernel: thread t of a CTA always sees the channels (4 t + j) mod 18 of
-// its 64-pixel tiles, so the four channels' (m, M - m, 1 / (M - m), mask) live in registers; every element has one
-// precomputed destination per output (keypoint_heatmaps / segmentation_masks slot, normalised-map slot).  The first
-// trip's logits are requested before the wait on pass 1 (they do not depend on it).
-__global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float *__restrict__ hml, const int npix,
-                                                                     const int tiles_per_img, float *__restrict__ kh,
-                                                                     float *__restrict__ seg,
-                                                                     const float *__restrict__ minmax,
-                                                                     float *__restrict__ nh)
-{
-    const int img = blockIdx.y, tid = threadIdx.x;
-    pdl_trigger();
-    bool is_kp[4];
-    int off[4], noff[4];                   // element offsets inside tile 0 of this image: 32-bit, four CTAs per SM
-    int ch[4];
-    float *kh_img = kh + (size_t)img * npix * kNK;
-    float *seg_img = seg ? seg + (size_t)img * npix : nullptr;
-    float *nh_img = nh + (size_t)img * npix * kPadCh;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int e = 4 * tid + j, p = e / kCH;
-        ch[j] = e - p * kCH;
-        is_kp[j] = ch[j] < kNK;
-        off[j] = is_kp[j] ? p * kNK + ch[j] : p;
-        noff[j] = p * kPadCh + ch[j];
-    }
-    const float4 *src = reinterpret_cast<const float4 *>(hml + (size_t)img * npix * kCH);
-    int tile = blockIdx.x;
-    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
-    if (tile < tiles_per_img) {
-        qa = __ldcs(src + (size_t)tile * kHmThreads + tid);
-        if (tile + (int)gridDim.x < tiles_per_img) qb = __ldcs(src + (size_t)(tile + gridDim.x) * kHmThreads + tid);
-    }
-    pdl_wait();                                        // pass 1 (min / max) has completed
-    float m[4], d[4], rcp[4], mask[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float lo = is_kp[j] ? __ldg(minmax + ((size_t)img * kNK + ch[j]) * 2) : 0.0f;
-        const float hi = is_kp[j] ? __ldg(minmax + ((size_t)img * kNK + ch[j]) * 2 + 1) : 1.0f;
-        m[j] = lo;
-        d[j] = fsub(hi, lo);
-        rcp[j] = range_rcp(d[j]);
-        mask[j] = hi > 0.2f ? 1.0f : 0.0f;
-    }
-    for (; tile < tiles_per_img; tile += 2 * gridDim.x) {
-        const int tile2 = tile + gridDim.x;
-        const bool two = tile2 < tiles_per_img;
-        const float va[4] = {qa.x, qa.y, qa.z, qa.w}, vb[4] = {qb.x, qb.y, qb.z, qb.w};
-        // next trip's loads in flight while this one is evaluated
-        const int nt = tile + 2 * gridDim.x, nt2 = nt + gridDim.x;
-        if (nt < tiles_per_img) qa = __ldcs(src + (size_t)nt * kHmThreads + tid);
-        if (nt2 < tiles_per_img) qb = __ldcs(src + (size_t)nt2 * kHmThreads + tid);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float sa, sb;
-            exact_sigmoidf_pair(va[j], vb[j], sa, sb);
-            if (is_kp[j]) {
-                kh_img[(size_t)tile * (kHmPix * kNK) + off[j]] = sa;
-                nh_img[(size_t)tile * (kHmPix * kPadCh) + noff[j]] = normalise_tap(sa, m[j], d[j], rcp[j], mask[j]);
-                if (two) {
-                    kh_img[(size_t)tile2 * (kHmPix * kNK) + off[j]] = sb;
-                    nh_img[(size_t)tile2 * (kHmPix * kPadCh) + noff[j]] = normalise_tap(sb, m[j], d[j], rcp[j], mask[j]);
-                }
-            } else if (seg_img) {
-                seg_img[(size_t)tile * kHmPix + off[j]] = va[j];
-                if (two) seg_img[(size_t)tile2 * kHmPix + off[j]] = vb[j];
-            }
+    float m = 0.0f, d = 1.0f, rcp = 1.0f, mask = 0.0f;
+    if (is_kp) {
+        const float hi = exact_sigmoidf(key_float(s_max[c]));
+        m = exact_sigmoidf(key_float(s_min[c]));
+        d = fsub(hi, m);
+        rcp = range_rcp(d);
+        mask = hi > 0.2f ? 1.0f : 0.0f;
+        if (blockIdx.x == 0 && p0 == 0) {
+            minmax[((size_t)img * kNK + c) * 2] = m;
+            minmax[((size_t)img * kNK + c) * 2 + 1] = hi;
         }
     }
+    // The reciprocal shortcut of div_by_range holds for a == 0 or a >= 1e-30 (a = kh - m); with m >= 1e-22 the smallest
+    // non-zero difference of two floats >= m is far above that, so the per-value test collapses to this per-thread flag
+    // (false for ordinary channels: the loop body is then straight-line code).
+    const bool careful = rcp == 0.0f || m < 1e-22f;
+    for (; tile < tiles_per_img; tile += 2 * gridDim.x) {
+        const bool two = tile + (int)gridDim.x < tiles_per_img;
+        float xa[kPerThread], xb[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) { xa[k] = va[k]; xb[k] = vb[k]; }
+        {   // next trip's loads in flight while this one is evaluated
+            const int nt = tile + 2 * gridDim.x;
+            sa += 2 * g * (kHmPix * kCH);
+            sb = (nt + (int)gridDim.x < tiles_per_img) ? sb + 2 * g * (kHmPix * kCH) : sa;
+            if (nt < tiles_per_img) {
+#pragma unroll
+                for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
+            }
+        }
+        float ya[kPerThread], yb[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) exact_sigmoidf_pair(xa[k], xb[k], ya[k], yb[k]);
+        if (is_kp) {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                float qa, qb;
+                if (careful) {
+                    qa = normalise_tap(ya[k], m, d, rcp, mask);
+                    qb = normalise_tap(yb[k], m, d, rcp, mask);
+                } else {                                     // div_by_range's shortcut, unconditionally
+                    const float aa = fsub(ya[k], m), ab = fsub(yb[k], m);
+                    const float q0a = fmul(aa, rcp), q0b = fmul(ab, rcp);
+                    qa = fmul(__fmaf_rn(__fmaf_rn(-q0a, d, aa), rcp, q0a), mask);
+                    qb = fmul(__fmaf_rn(__fmaf_rn(-q0b, d, ab), rcp, q0b), mask);
+                }
+                oa[k * (16 * kNK)] = ya[k];
+                na[k * (16 * kPadCh)] = qa;
+                if (two) {
+                    ob[k * (16 * kNK)] = yb[k];
+                    nb[k * (16 * kPadCh)] = qb;
+                }
+            }
+        } else if (oa) {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                oa[k * 16] = xa[k];
+                if (two) ob[k * 16] = xb[k];
+            }
+        }
+        if (oa) { oa += 2 * g * ostep; ob += 2 * g * ostep; }
+        na += 2 * g * (kHmPix * kPadCh); nb += 2 * g * (kHmPix * kPadCh);
+    }
 }
 
-// crop_and_resize of the PADDED normalised map (the path of mpn_run): same geometry table as crop_kernel below, but every
-// thread takes one (crop pixel, group of 4 channels): four aligned 16-byte tap loads, 12 lerps, and the four results go
-// to a shared-memory image of the band, which is then written out in memory order as 16-byte (fp32) and 8-byte (bf16)
-// vectors.
-struct __align__(16) PixTabP {
-    int p_tl, p_tr, p_bl, p_br;      // source pixel indices of the four taps; p_tl < 0: extrapolated (output 0)
-    float lx, ly, pad0, pad1;
+// crop_and_resize of the PADDED normalised map (the path of mpn_run wherever that map exists): one person per blockIdx.x,
+// a band of ROWS crop rows per blockIdx.y.  The sampling geometry is separable -- in_y depends on the crop row only, in_x
+// on the crop column only (the op's own fp32 operation order) -- and the work is laid out along that split: a thread owns
+// one (crop column, group of 4 channels) for the whole band, keeps its column's two source offsets and lerp weight in
+// registers, and walks the band's rows; per row it reads the row's entry (one broadcast 16-byte shared-memory load), issues
+// four aligned 16-byte tap loads (base pointer + row offset), does the 12 lerps and drops the four results into a
+// shared-memory image of the band, which is then written out in memory order as 16-byte (fp32) and 8-byte (bf16) vectors.
+// No division, no per-item index arithmetic: crop size, band height and block size are compile-time constants (the
+// runtime-sized one-item-per-thread version spent two thirds of its issue slots on index arithmetic).
+constexpr int kCropRows = 8;          // crop rows per CTA
+struct __align__(16) AxisTab {
+    unsigned lo, hi;                  // offsets of the two source rows (row * ww * 5), in 16-byte units
+    float w;                          // lerp weight towards `hi`
+    unsigned valid;                   // 0: outside the source map (extrapolation value 0)
 };
-constexpr int kCropPBands = 14;
-constexpr int kCropPMaxPix = 160;     // 4 rows x 36 columns = 144 pixels per band
 
-__global__ void __launch_bounds__(256) crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww,
-                                                          const float *__restrict__ boxes, const int *__restrict__ box_ind,
-                                                          const int *__restrict__ n_dev, const int n_host, const int crop_h,
-                                                          const int crop_w, float *__restrict__ out_f32,
-                                                          __nv_bfloat16 *__restrict__ out_bf16)
+template <int CH, int CW, int ROWS>
+__global__ void __launch_bounds__((CW * kGroups + 31) / 32 * 32)
+crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, const float *__restrict__ boxes,
+                   const int *__restrict__ box_ind, const int *__restrict__ n_dev, const int n_host,
+                   float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
 {
-    __shared__ PixTabP s_tab[kCropPMaxPix];
-    __shared__ __align__(16) float s_out[kCropPMaxPix * kNK];
-    const int n = blockIdx.x;
+    constexpr int kThreads = (CW * kGroups + 31) / 32 * 32;          // 192 for 36 columns: 180 of them own a (column, group)
+    constexpr int kPix = ROWS * CW, kOut4 = kPix * kNK / 4;
+    static_assert(CH % ROWS == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
+    __shared__ AxisTab s_y[ROWS];
+    __shared__ __align__(16) float s_out[kPix * kNK];
+    const int n = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
     pdl_wait();                                        // normalised map and person list are complete
     const int N = n_dev ? *n_dev : n_host;
     if (n >= N) return;
-    const int rows_per_band = (crop_h + gridDim.y - 1) / gridDim.y;
-    const int cy0 = blockIdx.y * rows_per_band, cy1 = min(crop_h, cy0 + rows_per_band);
-    if (cy0 >= cy1) return;
-    const int npix = (cy1 - cy0) * crop_w;
+    const int cy0 = blockIdx.y * ROWS;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
     const int b = __ldg(box_ind + n);
-    const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
     const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
-    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-        const int cy = cy0 + p / crop_w, cx = p % crop_w;
-        float in_y, in_x;
-        if (crop_h > 1) {
-            const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(crop_h - 1));
-            in_y = fadd(fmul(y1, hm1), fmul((float)cy, hs));
+    if (tid < ROWS) {                                  // the band's rows (create_pb.py:106-109, crop_and_resize_op.cc)
+        const float y1 = box.x, y2 = box.z;
+        float in_y;
+        if (CH > 1) {
+            const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(CH - 1));
+            in_y = fadd(fmul(y1, hm1), fmul((float)(cy0 + tid), hs));
         } else {
             in_y = fmul(fmul(0.5f, fadd(y1, y2)), hm1);
         }
-        if (crop_w > 1) {
-            const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(crop_w - 1));
+        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+        AxisTab t;
+        t.valid = !(in_y < 0.0f || in_y > hm1) ? 1u : 0u;
+        t.lo = t.valid ? (unsigned)(top * ww * kGroups) : 0u; t.hi = t.valid ? (unsigned)(bot * ww * kGroups) : 0u;
+        t.w = fsub(in_y, (float)top);
+        s_y[tid] = t;
+    }
+    // this thread's column
+    const int cx = min(tid / kGroups, CW - 1), g = tid - (tid / kGroups) * kGroups;
+    const bool owner = tid < CW * kGroups;
+    float in_x;
+    {
+        const float x1 = box.y, x2 = box.w;
+        if (CW > 1) {
+            const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(CW - 1));
             in_x = fadd(fmul(x1, wm1), fmul((float)cx, ws));
         } else {
             in_x = fmul(fmul(0.5f, fadd(x1, x2)), wm1);
         }
-        PixTabP t;
-        const bool valid = !(in_y < 0.0f || in_y > hm1 || in_x < 0.0f || in_x > wm1);
-        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
-        const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
-        t.p_tl = valid ? top * ww + left : -1;
-        t.p_tr = valid ? top * ww + right : 0;
-        t.p_bl = valid ? bot * ww + left : 0;
-        t.p_br = valid ? bot * ww + right : 0;
-        t.ly = fsub(in_y, (float)top); t.lx = fsub(in_x, (float)left);
-        t.pad0 = 0.0f; t.pad1 = 0.0f;
-        s_tab[p] = t;
     }
+    const bool x_valid = !(in_x < 0.0f || in_x > wm1);
+    const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
+    const float lx = fsub(in_x, (float)left);
+    const float4 *img = reinterpret_cast<const float4 *>(src + (size_t)b * hh * ww * kPadCh);
+    unsigned xl = x_valid ? (unsigned)(left * kGroups + g) : 0u, xr = x_valid ? (unsigned)(right * kGroups + g) : 0u;
+    asm volatile("" : "+r"(xl), "+r"(xr));             // keep the two column offsets in registers (no rematerialisation)
     __syncthreads();
-    const float *img = src + (size_t)b * hh * ww * kPadCh;
-    const int total = npix * kGroups;
-    for (int f = threadIdx.x; f < total; f += blockDim.x) {
-        const int p = f / kGroups, g = f - p * kGroups;
-        const int4 tp = *reinterpret_cast<const int4 *>(&s_tab[p].p_tl);
-        const float2 w = *reinterpret_cast<const float2 *>(&s_tab[p].lx);
-        float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (tp.x >= 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.x * kPadCh) + g);
-            const float4 bq = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.y * kPadCh) + g);
-            const float4 cq = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.z * kPadCh) + g);
-            const float4 d = __ldg(reinterpret_cast<const float4 *>(img + (size_t)tp.w * kPadCh) + g);
-            const float tl[4] = {a.x, a.y, a.z, a.w}, tr[4] = {bq.x, bq.y, bq.z, bq.w};
-            const float bl[4] = {cq.x, cq.y, cq.z, cq.w}, br[4] = {d.x, d.y, d.z, d.w};
+    if (owner) {
+        float *so = s_out + cx * kNK + 4 * g;
+#pragma unroll 4
+        for (int r = 0; r < ROWS; ++r) {
+            const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
+            float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (ty.w != 0u && x_valid) {
+                const float ly = __uint_as_float(ty.z);
+                const float4 a = __ldg(img + (ty.x + xl)), bq = __ldg(img + (ty.x + xr));
+                const float4 cq = __ldg(img + (ty.y + xl)), d = __ldg(img + (ty.y + xr));
+                const float tl[4] = {a.x, a.y, a.z, a.w}, tr[4] = {bq.x, bq.y, bq.z, bq.w};
+                const float bl[4] = {cq.x, cq.y, cq.z, cq.w}, br[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float tpv = fadd(tl[k], fmul(fsub(tr[k], tl[k]), w.x));
-                const float btv = fadd(bl[k], fmul(fsub(br[k], bl[k]), w.x));
-                r[k] = fadd(tpv, fmul(fsub(btv, tpv), w.y));
+                for (int k = 0; k < 4; ++k) {
+                    const float tpv = fadd(tl[k], fmul(fsub(tr[k], tl[k]), lx));
+                    const float btv = fadd(bl[k], fmul(fsub(br[k], bl[k]), lx));
+                    o[k] = fadd(tpv, fmul(fsub(btv, tpv), ly));
+                }
+            }
+            so[r * (CW * kNK)] = o[0];
+            if (g < kGroups - 1) {                     // group 4 holds channel 16 only
+                so[r * (CW * kNK) + 1] = o[1]; so[r * (CW * kNK) + 2] = o[2]; so[r * (CW * kNK) + 3] = o[3];
             }
         }
-        float *so = s_out + p * kNK + 4 * g;
-        so[0] = r[0];
-        if (g < kGroups - 1) { so[1] = r[1]; so[2] = r[2]; so[3] = r[3]; }      // group 4 holds channel 16 only
     }
     __syncthreads();
-    const int D = crop_h * crop_w * kNK;
-    const size_t o0 = (size_t)n * D + (size_t)cy0 * crop_w * kNK;     // multiple of 4 floats (launch_crop checks)
-    const int n4 = npix * kNK / 4;
-    for (int f = threadIdx.x; f < n4; f += blockDim.x) {
-        const float4 v = reinterpret_cast<const float4 *>(s_out)[f];
-        if (out_f32) reinterpret_cast<float4 *>(out_f32 + o0)[f] = v;
-        if (out_bf16) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 u;
-            u.x = *reinterpret_cast<const unsigned *>(&lo);
-            u.y = *reinterpret_cast<const unsigned *>(&hi);
-            reinterpret_cast<uint2 *>(out_bf16 + o0)[f] = u;
+    const size_t o0 = ((size_t)n * CH + cy0) * (CW * kNK);           // multiple of 4 floats
+#pragma unroll
+    for (int it = 0; it < (kOut4 + kThreads - 1) / kThreads; ++it) {
+        const int f = it * kThreads + tid;
+        if (f < kOut4) {
+            const float4 v = reinterpret_cast<const float4 *>(s_out)[f];
+            if (out_f32) reinterpret_cast<float4 *>(out_f32 + o0)[f] = v;
+            if (out_bf16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u;
+                u.x = *reinterpret_cast<const unsigned *>(&lo);
+                u.y = *reinterpret_cast<const unsigned *>(&hi);
+                reinterpret_cast<uint2 *>(out_bf16 + o0)[f] = u;
+            }
         }
     }
 }
@@ -746,28 +754,30 @@ int launch_heatmap_head(const float *x, const float *w, const float *bias, int B
     return launches;
 }
 
-// pass 1 of the two-pass form: (min, max) of the activations from the min / max of the logits -> minmax_ws [B, 17, 2]
-int launch_logit_minmax(const float *hml, int B, int hh, int ww, float *minmax_ws, int *partial_ws, int partial_chunks_cap,
-                        unsigned int *counter_ws, int slots, cudaStream_t s)
+// pass 1 of the two-pass form: per-CTA (min, max) of the logits -> partial_ws [B, *n_chunks, 17, 2] (ordered keys)
+int launch_logit_minmax(const float *hml, int B, int hh, int ww, int *partial_ws, int partial_chunks_cap, int slots,
+                        int *n_chunks, cudaStream_t s)
 {
     const int npix = hh * ww, tiles = (npix + kHmPix - 1) / kHmPix;
     int per_img = wave_chunks_per_image(slots, B, tiles, 4);
     if (per_img > partial_chunks_cap) per_img = partial_chunks_cap;
+    *n_chunks = per_img;
     prof_mark(s, "logit_minmax");
-    logit_minmax_kernel<<<dim3(per_img, B), kHmThreads, 0, s>>>(hml, npix, tiles, reinterpret_cast<unsigned *>(partial_ws),
-                                                                counter_ws, minmax_ws);
+    logit_minmax_kernel<<<dim3(per_img, B), kHmThreads, 0, s>>>(hml, npix, tiles, reinterpret_cast<unsigned *>(partial_ws));
     return 1;
 }
 
-// pass 2: keypoint_heatmaps, segmentation_masks and the padded normalised map in one pass over the logits
-int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const float *minmax_ws, float *nh,
-                        float *minmax_out, int slots, cudaStream_t s)
+// pass 2: keypoint_heatmaps, segmentation_masks, the padded normalised map and minmax_ws [B, 17, 2] in one pass over the
+// logits (n_chunks: what pass 1 reported)
+int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, float *seg, const int *partial_ws, int n_chunks,
+                        float *minmax_ws, float *nh, float *minmax_out, int slots, cudaStream_t s)
 {
     const int npix = hh * ww, tiles = (npix + kHmPix - 1) / kHmPix;
     const int per_img = wave_chunks_per_image(slots, B, tiles, 2);
     int launches = 1;
     prof_mark(s, "heatmap_norm");
-    launch_k(heatmap_norm_kernel, dim3(per_img, B), dim3(kHmThreads), 0, s, true, hml, npix, tiles, kh, seg, minmax_ws, nh);
+    launch_k(heatmap_norm_kernel, dim3(per_img, B), dim3(kHmThreads), 0, s, true, hml, npix, tiles, kh, seg,
+             reinterpret_cast<const unsigned *>(partial_ws), n_chunks, minmax_ws, nh);
     if (minmax_out) {
         const int nmm = B * kNK * 2;
         minmax_copy_kernel<<<(nmm + 255) / 256, 256, 0, s>>>(minmax_ws, minmax_out, nmm);
@@ -794,21 +804,18 @@ int launch_crop(const float *src, const float *minmax, int hh, int ww, const flo
     return 1;
 }
 
-bool crop_padded_supported(int crop_h, int crop_w)
-{
-    const int rows = (crop_h + kCropPBands - 1) / kCropPBands;
-    return rows * crop_w <= kCropPMaxPix && (rows * crop_w * kNK) % 4 == 0 && (crop_h * crop_w * kNK) % 4 == 0;
-}
+// the padded crop kernel is compiled for the reference's crop size (create_pb.py:19); other sizes take crop_kernel
+bool crop_padded_supported(int crop_h, int crop_w) { return crop_h == 56 && crop_w == 36; }
 
 int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,
                        int n_max, int crop_h, int crop_w, float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
     if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
-    dim3 grid(n_max, kCropPBands);
+    dim3 grid(n_max, 56 / kCropRows);
     prof_mark(s, "crop");
-    launch_k(crop_padded_kernel, grid, dim3(256), 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host, crop_h, crop_w,
-             crops_f32, crops_bf16);
+    launch_k(crop_padded_kernel<56, 36, kCropRows>, grid, dim3((36 * kGroups + 31) / 32 * 32), 0, s, true, nh, hh, ww, boxes,
+             box_ind, n_dev, n_host, crops_f32, crops_bf16);
     return 1;
 }
 
