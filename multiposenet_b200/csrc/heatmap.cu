@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float
 // shared-memory image of the band, which is then written out in memory order as 16-byte (fp32) and 8-byte (bf16) vectors.
 // No division, no per-item index arithmetic: crop size, band height and block size are compile-time constants (the
 // runtime-sized one-item-per-thread version spent two thirds of its issue slots on index arithmetic).
-constexpr int kCropRows = 8;          // crop rows per CTA
 struct __align__(16) AxisTab {
     unsigned lo, hi;                  // offsets of the two source rows (row * ww * 5), in 16-byte units
     float w;                          // lerp weight towards `hi`
@@ -443,11 +442,13 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
     const int n = blockIdx.x, tid = threadIdx.x;
     pdl_trigger();
     pdl_wait();                                        // normalised map and person list are complete
-    const int N = n_dev ? *n_dev : n_host;
+    // person count, box and image index in ONE round trip (rows past the count are allocated, their contents unused)
+    const float4 box = __ldcg(reinterpret_cast<const float4 *>(boxes) + n);
+    const int b_raw = __ldcg(box_ind + n);
+    const int N = n_dev ? __ldcg(n_dev) : n_host;
     if (n >= N) return;
+    const int b = b_raw;
     const int cy0 = blockIdx.y * ROWS;
-    const float4 box = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
-    const int b = __ldg(box_ind + n);
     const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
     if (tid < ROWS) {                                  // the band's rows (create_pb.py:106-109, crop_and_resize_op.cc)
         const float y1 = box.x, y2 = box.z;
@@ -487,7 +488,7 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
     __syncthreads();
     if (owner) {
         float *so = s_out + cx * kNK + 4 * g;
-#pragma unroll 4
+#pragma unroll 4                    // four rows' taps (16 loads) in flight
         for (int r = 0; r < ROWS; ++r) {
             const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
             float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -812,10 +813,16 @@ int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, cons
 {
     if (n_max <= 0) return 0;
     if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
-    dim3 grid(n_max, 56 / kCropRows);
+    // Rows per CTA: 4 (all of a thread's taps in flight at once, twice the CTAs) while the call is small enough to be a
+    // latency problem -- at most one resident wave of CTAs -- 8 (half the per-CTA prologue per value) beyond.
     prof_mark(s, "crop");
-    launch_k(crop_padded_kernel<56, 36, kCropRows>, grid, dim3((36 * kGroups + 31) / 32 * 32), 0, s, true, nh, hh, ww, boxes,
-             box_ind, n_dev, n_host, crops_f32, crops_bf16);
+    const dim3 block((36 * kGroups + 31) / 32 * 32);
+    if (n_max <= 640)
+        launch_k(crop_padded_kernel<56, 36, 4>, dim3(n_max, 14), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
+                 crops_f32, crops_bf16);
+    else
+        launch_k(crop_padded_kernel<56, 36, 8>, dim3(n_max, 7), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
+                 crops_f32, crops_bf16);
     return 1;
 }
 
