@@ -529,6 +529,8 @@ int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int3
         return fail(h, MPN_ERR_UNSUPPORTED, "heatmap pixel count must be a multiple of 64 (it is for images divisible by 128)");
     if ((long long)hm_height * hm_width > h->max_hm_pix)     // the per-CTA min / max array is sized for the handle's capacity
         return fail(h, MPN_ERR_CAPACITY, "heatmap %dx%d exceeds the handle's capacity of %d pixels", hm_height, hm_width, h->max_hm_pix);
+    if (reinterpret_cast<uintptr_t>(heatmap_logits) % 16 != 0)          // tiles arrive by 16-byte-granular bulk copies
+        return fail(h, MPN_ERR_INVALID_ARGUMENT, "heatmap_logits must be 16-byte aligned");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     return launched(h, launch_heatmaps(heatmap_logits, batch, hm_height, hm_width, keypoint_heatmaps, segmentation_masks,
                                        h->minmax_ws, minmax, h->hm_partial, h->hm_counter, h->waves.one_pass, (cudaStream_t)stream),

@@ -12,6 +12,7 @@
 // channel t mod 18 (pixels t / 18 + 16 k) -- one channel per thread, its running min / max or its normalisation constants
 // in a handful of registers -- and a warp's 32 lanes touch 32 consecutive floats in every load and every store (one
 // wavefront each; an earlier float4-per-thread map made every scalar store a stride-4 access of four wavefronts).
+#include "bulk_copy.cuh"
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -60,6 +61,7 @@ __device__ __forceinline__ void publish_minmax(int *s_min, int *s_max, int *s_la
 }
 
 constexpr int kPerThread = kHmPix * kCH / kHmThreads;      // 4 elements of a tile per thread
+constexpr int kRingTiles = 6;                              // tiles per CTA in the bulk-copy ring (even: two per trip)
 
 // One pass (maps that take the per-tap crop path): activation, split, per-(image, channel) min / max.  grid = (chunks per
 // image, B).  Outputs are written straight from registers; per-CTA (min, max) go to a small partial array; the last CTA of
@@ -72,28 +74,53 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
 {
     __shared__ int s_min[kNK], s_max[kNK];
     __shared__ int s_last;
+    __shared__ __align__(128) float s_tile[kRingTiles][kHmPix * kCH];
+    __shared__ unsigned long long s_bar[kRingTiles];
     const int img = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
     const int c = tid % kCH, p0 = tid / kCH;
     const bool is_kp = c < kNK;
     float mn = __int_as_float(0x7f800000), mx = 0.0f;
     if (tid < kNK) { s_min[tid] = 0x7f800000; s_max[tid] = 0; }
-    // Running pointers (tile blockIdx.x and tile blockIdx.x + gridDim.x, advanced by two grid strides per trip): every
-    // load and store of the loop is base + immediate.  A keypoint thread writes keypoint_heatmaps, a mask-channel
-    // thread segmentation_masks -- one output pointer pair per thread, the role fixed for the thread's life.
+    // The CTA's tiles (blockIdx.x, + gridDim.x, ...) arrive through a ring of kRingTiles bulk copies (bulk_copy.cuh): four
+    // to six tiles -- 18 to 27 KB per CTA, four CTAs per SM -- are in flight while two are evaluated, which is what the
+    // stream needs against HBM latency (eight register loads per thread and trip kept it at half of that).
+    // Output pointers run along (tile j and tile j + 1 of this CTA, advanced by two grid strides per trip): every store is
+    // base + immediate.  A keypoint thread writes keypoint_heatmaps, a mask-channel thread segmentation_masks.
     const size_t g = gridDim.x;
-    const float *sa = hml + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix) * kCH + tid, *sb = sa + g * (kHmPix * kCH);
+    const float *img_src = hml + (size_t)img * npix * kCH;
+    const int n_mine = (int)blockIdx.x < tiles_per_img ? (tiles_per_img - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (tid == 0) {
+        bulk_barrier_init(s_bar, kRingTiles);
+        for (int j = 0; j < kRingTiles && j < n_mine; ++j)
+            bulk_fetch(s_tile[j], img_src + ((size_t)blockIdx.x + j * g) * (kHmPix * kCH), kHmPix * kCH * 4, &s_bar[j]);
+    }
     float *oa = is_kp ? kh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kNK + c
                       : (seg ? seg + (size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0 : nullptr);
     const size_t ostep = is_kp ? kHmPix * kNK : kHmPix;
     float *ob = oa ? oa + g * ostep : nullptr;
+    __syncthreads();                                   // barriers initialised, s_min / s_max reset
     // npix is a multiple of 64 on this path (images are multiples of 128): every tile is full.  Two tiles per trip.
-    for (int tile = blockIdx.x; tile < tiles_per_img; tile += 2 * gridDim.x) {
-        const bool two = tile + (int)gridDim.x < tiles_per_img;
-        if (!two) sb = sa;                                   // no second tile: the first one again (min / max unchanged)
+    for (int j = 0; j < n_mine; j += 2) {
+        const bool two = j + 1 < n_mine;
+        const int sl_a = j % kRingTiles, sl_b = (j + 1) % kRingTiles;
+        bulk_wait(&s_bar[sl_a], (unsigned)(j / kRingTiles) & 1u);
+        if (two) bulk_wait(&s_bar[sl_b], (unsigned)((j + 1) / kRingTiles) & 1u);
         float va[kPerThread], vb[kPerThread];
 #pragma unroll
-        for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
+        for (int k = 0; k < kPerThread; ++k) {
+            va[k] = s_tile[sl_a][k * kHmThreads + tid];
+            vb[k] = two ? s_tile[sl_b][k * kHmThreads + tid] : va[k];      // no second tile: the first again (min / max unchanged)
+        }
+        __syncthreads();                               // both slots have been read by everybody: refill them
+        if (tid == 0) {
+            if (j + kRingTiles < n_mine)
+                bulk_fetch(s_tile[sl_a], img_src + ((size_t)blockIdx.x + (j + kRingTiles) * g) * (kHmPix * kCH), kHmPix * kCH * 4,
+                           &s_bar[sl_a]);
+            if (j + 1 + kRingTiles < n_mine)
+                bulk_fetch(s_tile[sl_b], img_src + ((size_t)blockIdx.x + (j + 1 + kRingTiles) * g) * (kHmPix * kCH),
+                           kHmPix * kCH * 4, &s_bar[sl_b]);
+        }
         float ya[kPerThread], yb[kPerThread];
 #pragma unroll
         for (int k = 0; k < kPerThread; ++k) {
@@ -103,17 +130,16 @@ __global__ void __launch_bounds__(kHmThreads) heatmap_kernel(const float *__rest
         if (is_kp) {
 #pragma unroll
             for (int k = 0; k < kPerThread; ++k) {
-                oa[k * (16 * kNK)] = ya[k];
-                if (two) ob[k * (16 * kNK)] = yb[k];
+                __stcs(oa + k * (16 * kNK), ya[k]);               // outputs are not read again on the device: streaming stores
+                if (two) __stcs(ob + k * (16 * kNK), yb[k]);
             }
         } else if (oa) {
 #pragma unroll
             for (int k = 0; k < kPerThread; ++k) {
-                oa[k * 16] = va[k];
-                if (two) ob[k * 16] = vb[k];
+                __stcs(oa + k * 16, va[k]);
+                if (two) __stcs(ob + k * 16, vb[k]);
             }
         }
-        sa += 2 * g * (kHmPix * kCH); sb += 2 * g * (kHmPix * kCH);
         if (oa) { oa += 2 * g * ostep; ob += 2 * g * ostep; }
     }
     __syncthreads();
@@ -316,26 +342,28 @@ __global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float
                                                                      float *__restrict__ nh)
 {
     __shared__ unsigned s_min[kNK], s_max[kNK];
+    __shared__ __align__(128) float s_tile[kRingTiles][kHmPix * kCH];
+    __shared__ unsigned long long s_bar[kRingTiles];
     const int img = blockIdx.y, tid = threadIdx.x;
     pdl_trigger();
     const int c = tid % kCH, p0 = tid / kCH;
     const bool is_kp = c < kNK;
     if (tid < kNK) { s_min[tid] = kKeyPosInf; s_max[tid] = kKeyNegInf; }
-    // running pointers, as in heatmap_kernel; a keypoint thread also owns a slot of the padded normalised map
+    // tile ring and running output pointers as in heatmap_kernel; a keypoint thread also owns a slot of the padded
+    // normalised map.  The first tiles are requested before the wait on pass 1 (they do not depend on it).
     const size_t g = gridDim.x;
-    const float *sa = hml + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix) * kCH + tid, *sb = sa + g * (kHmPix * kCH);
+    const float *img_src = hml + (size_t)img * npix * kCH;
+    const int n_mine = (int)blockIdx.x < tiles_per_img ? (tiles_per_img - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (tid == 0) {
+        bulk_barrier_init(s_bar, kRingTiles);
+        for (int j = 0; j < kRingTiles && j < n_mine; ++j)
+            bulk_fetch(s_tile[j], img_src + ((size_t)blockIdx.x + j * g) * (kHmPix * kCH), kHmPix * kCH * 4, &s_bar[j]);
+    }
     float *oa = is_kp ? kh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kNK + c
                       : (seg ? seg + (size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0 : nullptr);
     const size_t ostep = is_kp ? kHmPix * kNK : kHmPix;
     float *ob = oa ? oa + g * ostep : nullptr;
     float *na = nh + ((size_t)img * npix + (size_t)blockIdx.x * kHmPix + p0) * kPadCh + c, *nb = na + g * (kHmPix * kPadCh);
-    int tile = blockIdx.x;
-    float va[kPerThread], vb[kPerThread];
-    {
-        if (!(tile + (int)gridDim.x < tiles_per_img)) sb = sa;
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
-    }
     __syncthreads();
     pdl_wait();                                        // pass 1 has completed
     if (is_kp) {
@@ -364,19 +392,25 @@ __global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float
     // non-zero difference of two floats >= m is far above that, so the per-value test collapses to this per-thread flag
     // (false for ordinary channels: the loop body is then straight-line code).
     const bool careful = rcp == 0.0f || m < 1e-22f;
-    for (; tile < tiles_per_img; tile += 2 * gridDim.x) {
-        const bool two = tile + (int)gridDim.x < tiles_per_img;
+    for (int j = 0; j < n_mine; j += 2) {
+        const bool two = j + 1 < n_mine;
+        const int sl_a = j % kRingTiles, sl_b = (j + 1) % kRingTiles;
+        bulk_wait(&s_bar[sl_a], (unsigned)(j / kRingTiles) & 1u);
+        if (two) bulk_wait(&s_bar[sl_b], (unsigned)((j + 1) / kRingTiles) & 1u);
         float xa[kPerThread], xb[kPerThread];
 #pragma unroll
-        for (int k = 0; k < kPerThread; ++k) { xa[k] = va[k]; xb[k] = vb[k]; }
-        {   // next trip's loads in flight while this one is evaluated
-            const int nt = tile + 2 * gridDim.x;
-            sa += 2 * g * (kHmPix * kCH);
-            sb = (nt + (int)gridDim.x < tiles_per_img) ? sb + 2 * g * (kHmPix * kCH) : sa;
-            if (nt < tiles_per_img) {
-#pragma unroll
-                for (int k = 0; k < kPerThread; ++k) { va[k] = __ldcs(sa + k * kHmThreads); vb[k] = __ldcs(sb + k * kHmThreads); }
-            }
+        for (int k = 0; k < kPerThread; ++k) {
+            xa[k] = s_tile[sl_a][k * kHmThreads + tid];
+            xb[k] = two ? s_tile[sl_b][k * kHmThreads + tid] : xa[k];
+        }
+        __syncthreads();                               // both slots have been read by everybody: refill them
+        if (tid == 0) {
+            if (j + kRingTiles < n_mine)
+                bulk_fetch(s_tile[sl_a], img_src + ((size_t)blockIdx.x + (j + kRingTiles) * g) * (kHmPix * kCH), kHmPix * kCH * 4,
+                           &s_bar[sl_a]);
+            if (j + 1 + kRingTiles < n_mine)
+                bulk_fetch(s_tile[sl_b], img_src + ((size_t)blockIdx.x + (j + 1 + kRingTiles) * g) * (kHmPix * kCH),
+                           kHmPix * kCH * 4, &s_bar[sl_b]);
         }
         float ya[kPerThread], yb[kPerThread];
 #pragma unroll
@@ -394,18 +428,18 @@ __global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float
                     qa = fmul(__fmaf_rn(__fmaf_rn(-q0a, d, aa), rcp, q0a), mask);
                     qb = fmul(__fmaf_rn(__fmaf_rn(-q0b, d, ab), rcp, q0b), mask);
                 }
-                oa[k * (16 * kNK)] = ya[k];
-                na[k * (16 * kPadCh)] = qa;
+                __stcs(oa + k * (16 * kNK), ya[k]);          // an output: not read again on the device
+                na[k * (16 * kPadCh)] = qa;                  // read by the crop kernel next: default policy
                 if (two) {
-                    ob[k * (16 * kNK)] = yb[k];
+                    __stcs(ob + k * (16 * kNK), yb[k]);
                     nb[k * (16 * kPadCh)] = qb;
                 }
             }
         } else if (oa) {
 #pragma unroll
             for (int k = 0; k < kPerThread; ++k) {
-                oa[k * 16] = xa[k];
-                if (two) ob[k * 16] = xb[k];
+                __stcs(oa + k * 16, xa[k]);
+                if (two) __stcs(ob + k * 16, xb[k]);
             }
         }
         if (oa) { oa += 2 * g * ostep; ob += 2 * g * ostep; }
@@ -518,13 +552,16 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
         const int f = it * kThreads + tid;
         if (f < kOut4) {
             const float4 v = reinterpret_cast<const float4 *>(s_out)[f];
-            if (out_f32) reinterpret_cast<float4 *>(out_f32 + o0)[f] = v;
+            // Streaming (evict-first) stores: in a crowded call the crops are hundreds of MB written once and read by the
+            // PRN much later, while the normalised map the taps come from (tens of MB, re-read by every person of an
+            // image) should be what stays in L2; in a small call nothing is evicted either way.
+            if (out_f32) __stcs(reinterpret_cast<float4 *>(out_f32 + o0) + f, v);
             if (out_bf16) {
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
                 uint2 u;
                 u.x = *reinterpret_cast<const unsigned *>(&lo);
                 u.y = *reinterpret_cast<const unsigned *>(&hi);
-                reinterpret_cast<uint2 *>(out_bf16 + o0)[f] = u;
+                __stcs(reinterpret_cast<uint2 *>(out_bf16 + o0) + f, u);
             }
         }
     }

@@ -33,6 +33,7 @@
 // handle accepts -- 17 * positions a multiple of 32 -- satisfies the bulk copy's 16-byte granularity.)
 #include <cstdlib>
 
+#include "bulk_copy.cuh"
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -97,7 +98,7 @@ struct ClusterStats {
 struct BlockScratch {
     float m[kThreads];                    // indexed by thread (q * 17 + c): conflict-free both ways (17 is odd)
     float s[kThreads];
-    unsigned short hits[kThreads];        // bit i: value i of the thread reaches the thread's maximum (exp == 1)
+    unsigned char first[kThreads];        // index (0..15) of the thread's first value that reaches its maximum (exp == 1)
     float gmax[kNK];
     int found;
     unsigned char rescan[kNK + 3];        // CTA 0: channel needs the exact rescan
@@ -125,22 +126,27 @@ __device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], i
     for (int i = 1; i < kMaxPerThread; ++i) m = fmaxf(m, v[i]);
     const float kLog2e = 1.4426950408889634f;
     const float m2 = m == -__int_as_float(0x7f800000) ? 0.0f : -m * kLog2e;    // empty partial: keep the exponents at -inf
-    float s = 0.0f;
-    unsigned hits = 0u;                                // bit i: exact_expf(v[i] - m) == 1.0f
+    // Walked from the last value to the first: `first` ends up as the lowest index whose logit reaches the thread's
+    // maximum under the recipe (one compare + one select per value), the sum is kept as a packed pair of running sums
+    // (even / odd values), added once at the end.
+    int first = kMaxPerThread;
+    f32x2 ss = f2_pack(0.0f, 0.0f);
     const f32x2 mm = f2_bcast(m), l2e = f2_bcast(kLog2e), mm2 = f2_bcast(m2);
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; i += 2) {       // two logits per FADD2 / FFMA2, same operations and order per lane
+    for (int i = kMaxPerThread - 2; i >= 0; i -= 2) {  // two logits per FADD2 / FFMA2, same operations per lane
         const f32x2 vv = f2_pack(v[i], v[i + 1]);
         float d0, d1, t0, t1;
         f2_unpack(f2_sub(vv, mm), d0, d1);
         f2_unpack(f2_fma(vv, l2e, mm2), t0, t1);
-        hits |= (d0 >= x0) ? (1u << i) : 0u;
-        hits |= (d1 >= x0) ? (2u << i) : 0u;
-        s = fadd(s, exp2f_approx(t0));
-        s = fadd(s, exp2f_approx(t1));
+        first = (d1 >= x0) ? i + 1 : first;
+        first = (d0 >= x0) ? i : first;
+        ss = f2_add(ss, f2_pack(exp2f_approx(t0), exp2f_approx(t1)));
     }
+    float s0, s1;
+    f2_unpack(ss, s0, s1);
+    const float s = fadd(s0, s1);
     const int me = q * kNK + c;                        // == threadIdx.x
-    sc.m[me] = m; sc.s[me] = s; sc.hits[me] = (unsigned short)hits;
+    sc.m[me] = m; sc.s[me] = s; sc.first[me] = (unsigned char)first;
     __syncthreads();
     {   // warp w = channel w: the 32 partials (q = lane) -> one
         const int src = lane * kNK + warp;
@@ -149,8 +155,8 @@ __device__ __forceinline__ void slab_partials(const float (&v)[kMaxPerThread], i
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
         float S = rescaled(sc.s[src], pm, M);
-        const unsigned h = sc.hits[src];
-        int F = (pm == M && h) ? p0 + lane + kLanes * (__ffs(h) - 1) : kNone;
+        const int h = sc.first[src];
+        int F = (pm == M && h < kMaxPerThread) ? p0 + lane + kLanes * h : kNone;
         const bool near = pm < M && fsub(pm, M) >= x0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {             // butterfly: a fixed summation tree
@@ -217,37 +223,10 @@ __device__ __forceinline__ void cluster_finish(const ClusterStats &st, int buf, 
 }
 
 // ---- streaming variant ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void slab_wait(unsigned long long *bar, unsigned parity)
-{
-    const unsigned addr = smem_addr(bar);
-    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
-        unsigned done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();      // a protocol bug is reported as a CUDA error instead of hanging the GPU
-}
-
-// one thread: request `bytes` (multiple of 16) of global memory into shared memory, completion on `bar`
-__device__ __forceinline__ void slab_fetch(float *dst, const float *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of dst are done (bar.sync)
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
+// PER: positions per CTA when known at compile time (504 for the reference's 56 x 36 crop: only the last of a thread's 16
+// loads then needs a bounds test, on the lane alone; the per-value tests of the general form were a quarter of the
+// kernel's instructions), 0 = derived from the runtime crop size.
+template <int PER>
 __global__ void __cluster_dims__(kCluster, 1, 1) __maxnreg__(40)
 keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__restrict__ n_dev, const int n_host,
                               const int crop_h, const int crop_w, float *__restrict__ scores,
@@ -260,16 +239,13 @@ keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__res
     const unsigned rank = cluster_rank();
     const int n_clusters = gridDim.x / kCluster;
     const int tid = threadIdx.x, c = tid % kNK, q = tid / kNK;
-    const int P = crop_h * crop_w;
-    const int per = (P + kCluster - 1) / kCluster;        // per * 17 * 4 bytes is a multiple of 16 (checked by the host)
+    const int P = PER > 0 ? PER * kCluster : crop_h * crop_w;
+    const int per = PER > 0 ? PER : (P + kCluster - 1) / kCluster;   // per * 17 * 4 bytes is a multiple of 16 (checked by the host)
     const int p0 = (int)rank * per, p1 = min(P, p0 + per);
     const int slab_floats = per * kNK;
     const unsigned bytes = (unsigned)max(p1 - p0, 0) * kNK * 4u;
     pdl_trigger();
-    if (tid == 0) {
-        for (int i = 0; i < kSlots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[i])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid == 0) bulk_barrier_init(s_bar, kSlots);
     pdl_wait();                           // the PRN has completed
     __syncthreads();
     const int N = n_dev ? *n_dev : n_host;
@@ -279,7 +255,7 @@ keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__res
     if (tid == 0 && bytes)
         for (int j = 0; j < kSlots - 1; ++j) {
             const long long nj = (long long)n + (long long)j * n_clusters;
-            if (nj < N) slab_fetch(s_slab + j * slab_floats, logits + (size_t)nj * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[j]);
+            if (nj < N) bulk_fetch(s_slab + j * slab_floats, logits + (size_t)nj * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[j]);
         }
     for (int it = 0; n < N; ++it, n += n_clusters) {       // uniform over the cluster
         const int slot = it % kSlots;
@@ -288,13 +264,15 @@ keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__res
         const long long n_ahead = (long long)n + (long long)(kSlots - 1) * n_clusters;
         if (tid == 0 && n_ahead < N && bytes) {
             const int sa = (it + kSlots - 1) % kSlots;
-            slab_fetch(s_slab + sa * slab_floats, logits + (size_t)n_ahead * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[sa]);
+            bulk_fetch(s_slab + sa * slab_floats, logits + (size_t)n_ahead * P * kNK + (size_t)p0 * kNK, bytes, &s_bar[sa]);
         }
-        if (bytes) slab_wait(&s_bar[slot], (unsigned)(it / kSlots) & 1u);
+        if (bytes) bulk_wait(&s_bar[slot], (unsigned)(it / kSlots) & 1u);
         float v[kMaxPerThread];
 #pragma unroll
-        for (int i = 0; i < kMaxPerThread; ++i)
-            v[i] = (p0 + q + kLanes * i < p1) ? src[tid + kThreads * i] : -__int_as_float(0x7f800000);
+        for (int i = 0; i < kMaxPerThread; ++i) {
+            const bool in = PER > 0 ? (kLanes * i + kLanes <= PER || q + kLanes * i < PER) : (p0 + q + kLanes * i < p1);
+            v[i] = in ? src[tid + kThreads * i] : -__int_as_float(0x7f800000);
+        }
         // partials of iteration it go to buffer it & 1 of CTA 0: CTA 0 read it last in iteration it - 2, i.e. before it
         // arrived at the barrier of iteration it - 1, which this CTA has already passed
         slab_partials(v, p0, q, c, tid >> 5, tid & 31, x0, sc, stats0, it & 1, rank);
@@ -308,13 +286,17 @@ keypoint_decode_stream_kernel(const float *__restrict__ logits, const int *__res
 
 }  // namespace
 
+constexpr int kPerDefault = 56 * 36 / kCluster;        // 504: the reference's crop (create_pb.py:19)
+
 int kpdecode_prepare(cudaStream_t s, int crop_h, int crop_w, int *resident_clusters)
 {
     exp_one_threshold_kernel<<<1, 1, 0, s>>>();
     if (cudaGetLastError() != cudaSuccess) return -1;
     // the streaming kernel's slab ring: sized for the default 56 x 36 crop and anything smaller
-    if (cudaFuncSetAttribute(keypoint_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSlabBytes) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(keypoint_decode_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSlabBytes) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(keypoint_decode_stream_kernel<kPerDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kStreamSlabBytes) != cudaSuccess)
         return -1;
     const int P = crop_h * crop_w, per = (P + kCluster - 1) / kCluster;
     if (P > kMaxPerThread * kLanes * kCluster || per % 4 != 0 || P % 4 != 0 || kSlots * per * kNK * 4 > kStreamSlabBytes) return -2;
@@ -322,7 +304,10 @@ int kpdecode_prepare(cudaStream_t s, int crop_h, int crop_w, int *resident_clust
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kCluster * 1024); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSlots * per * kNK * 4;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel, &cfg) != cudaSuccess || n < 1) n = 64;
+    const cudaError_t e = P == kPerDefault * kCluster
+                              ? cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel<kPerDefault>, &cfg)
+                              : cudaOccupancyMaxActiveClusters(&n, keypoint_decode_stream_kernel<0>, &cfg);
+    if (e != cudaSuccess || n < 1) n = 64;
     cudaGetLastError();
     *resident_clusters = n;
     return 0;
@@ -335,8 +320,12 @@ int launch_keypoint_decode(const float *logits, const int *n_dev, int n_host, in
     const int P = crop_h * crop_w, per = (P + kCluster - 1) / kCluster;
     const int clusters = n_max < resident_clusters ? n_max : resident_clusters;
     prof_mark(s, "keypoint_decode");
-    launch_k(keypoint_decode_stream_kernel, dim3(clusters * kCluster), dim3(kThreads), (size_t)(kSlots * per * kNK * 4), s, true,
-             logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
+    if (P == kPerDefault * kCluster)
+        launch_k(keypoint_decode_stream_kernel<kPerDefault>, dim3(clusters * kCluster), dim3(kThreads),
+                 (size_t)(kSlots * per * kNK * 4), s, true, logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
+    else
+        launch_k(keypoint_decode_stream_kernel<0>, dim3(clusters * kCluster), dim3(kThreads), (size_t)(kSlots * per * kNK * 4), s,
+                 true, logits, n_dev, n_host, crop_h, crop_w, scores, positions, argmax);
     return 1;
 }
 
