@@ -462,7 +462,13 @@ struct __align__(16) AxisTab {
     unsigned valid;                   // 0: outside the source map (extrapolation value 0)
 };
 
-template <int CH, int CW, int ROWS>
+// CACHE (large calls): the op's horizontal lerps tl + (tr - tl) lx of a source row do not depend on the crop row that
+// uses them, and consecutive crop rows share source rows (all of them whenever the box is less than twice as tall in
+// source pixels as the crop: a thread's last two horizontally interpolated rows stay in registers and are reused when
+// the next crop row asks for the same source row (the row ids come from the shared table: the test is uniform over the
+// CTA).  Same operations on the same operands, so the same bits, at half to a third of the tap loads -- the kernel is bound
+// by L1 wavefronts.  Small calls (latency, not throughput) keep all taps of a thread in flight instead (CACHE = false).
+template <int CH, int CW, int ROWS, bool CACHE>
 __global__ void __launch_bounds__((CW * kGroups + 31) / 32 * 32)
 crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, const float *__restrict__ boxes,
                    const int *__restrict__ box_ind, const int *__restrict__ n_dev, const int n_host,
@@ -522,22 +528,53 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
     __syncthreads();
     if (owner) {
         float *so = s_out + cx * kNK + 4 * g;
-#pragma unroll 4                    // four rows' taps (16 loads) in flight
+        float held[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};      // CACHE: the last top / bottom source rows
+        unsigned held_row[2] = {0xffffffffu, 0xffffffffu};
+        // one source row, horizontally interpolated at this thread's column: tl + (tr - tl) * lx per channel
+        auto hrow = [&](unsigned row, float (&h)[4]) {
+            const float4 a = __ldg(img + (row + xl)), bq = __ldg(img + (row + xr));
+            const float l[4] = {a.x, a.y, a.z, a.w}, rr[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = fadd(l[k], fmul(fsub(rr[k], l[k]), lx));
+        };
+#pragma unroll 4                    // CACHE = false: four rows' taps (16 loads) in flight
         for (int r = 0; r < ROWS; ++r) {
             const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
             float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (ty.w != 0u && x_valid) {
                 const float ly = __uint_as_float(ty.z);
-                const float4 a = __ldg(img + (ty.x + xl)), bq = __ldg(img + (ty.x + xr));
-                const float4 cq = __ldg(img + (ty.y + xl)), d = __ldg(img + (ty.y + xr));
-                const float tl[4] = {a.x, a.y, a.z, a.w}, tr[4] = {bq.x, bq.y, bq.z, bq.w};
-                const float bl[4] = {cq.x, cq.y, cq.z, cq.w}, br[4] = {d.x, d.y, d.z, d.w};
+                float tp[4], bt[4];
+                if (CACHE) {
+                    if (ty.x == held_row[0]) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float tpv = fadd(tl[k], fmul(fsub(tr[k], tl[k]), lx));
-                    const float btv = fadd(bl[k], fmul(fsub(br[k], bl[k]), lx));
-                    o[k] = fadd(tpv, fmul(fsub(btv, tpv), ly));
+                        for (int k = 0; k < 4; ++k) tp[k] = held[0][k];
+                    } else if (ty.x == held_row[1]) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tp[k] = held[1][k];
+                    } else {
+                        hrow(ty.x, tp);
+                    }
+                    if (ty.y == ty.x) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) bt[k] = tp[k];
+                    } else if (ty.y == held_row[1]) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) bt[k] = held[1][k];
+                    } else if (ty.y == held_row[0]) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) bt[k] = held[0][k];
+                    } else {
+                        hrow(ty.y, bt);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { held[0][k] = tp[k]; held[1][k] = bt[k]; }
+                    held_row[0] = ty.x; held_row[1] = ty.y;
+                } else {
+                    hrow(ty.x, tp);
+                    hrow(ty.y, bt);
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = fadd(tp[k], fmul(fsub(bt[k], tp[k]), ly));
             }
             so[r * (CW * kNK)] = o[0];
             if (g < kGroups - 1) {                     // group 4 holds channel 16 only
@@ -851,15 +888,16 @@ int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, cons
     if (n_max <= 0) return 0;
     if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
     // Rows per CTA: 4 (all of a thread's taps in flight at once, twice the CTAs) while the call is small enough to be a
-    // latency problem -- at most one resident wave of CTAs -- 8 (half the per-CTA prologue per value) beyond.
+    // latency problem -- at most one resident wave of CTAs -- 8 with the source-row cache (half the per-CTA prologue per
+    // value, a third to a half of the tap loads) beyond.
     prof_mark(s, "crop");
     const dim3 block((36 * kGroups + 31) / 32 * 32);
     if (n_max <= 640)
-        launch_k(crop_padded_kernel<56, 36, 4>, dim3(n_max, 14), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
-                 crops_f32, crops_bf16);
+        launch_k(crop_padded_kernel<56, 36, 4, false>, dim3(n_max, 14), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev,
+                 n_host, crops_f32, crops_bf16);
     else
-        launch_k(crop_padded_kernel<56, 36, 8>, dim3(n_max, 7), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
-                 crops_f32, crops_bf16);
+        launch_k(crop_padded_kernel<56, 36, 8, true>, dim3(n_max, 7), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev,
+                 n_host, crops_f32, crops_bf16);
     return 1;
 }
 

@@ -167,6 +167,17 @@ def test_crop_padded_bit_exact(weights, key, batch):
         assert_bits(f.cpu().numpy(), want, "padded crops")
         assert torch.equal(b16, f.to(torch.bfloat16))
         assert want.any()
+        # more than 640 boxes in one call: the large-call form of the kernel (8 rows per CTA, horizontally interpolated
+        # source rows kept in registers across crop rows) -- tall, flat, tiny, flipped and out-of-image boxes included
+        many, many_i = _extra_boxes(rng, B, 693)
+        many[7:107, 2] = many[7:107, 0] + rng.uniform(0.0, 0.05, 100).astype(np.float32)      # flat: many crop rows per source row
+        many[107:207, 2] = np.minimum(many[107:207, 0] + 0.9, 1.2)                            # tall: source rows skipped
+        boxes2, ind2 = np.concatenate([boxes, many]), np.concatenate([ind, many_i])
+        assert len(boxes2) > 640
+        want2 = oracle.crop_and_resize(kh, boxes2, ind2, (56, 36), mn, mx)
+        f2, b2 = det.crop_padded(nh, _cuda(boxes2), _cuda(ind2))
+        assert_bits(f2.cpu().numpy(), want2, "padded crops, large call")
+        assert torch.equal(b2, f2.to(torch.bfloat16))
     finally:
         det.close()
 

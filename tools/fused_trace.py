@@ -32,5 +32,15 @@ for rep in range(3):
         col = col[col > 0] - t0
         if col.size:
             print(f"  {names[slot]:24s} min {col.min() / 1e3:7.2f}  median {np.median(col) / 1e3:7.2f}  max {col.max() / 1e3:7.2f} us  ({col.size} CTAs)")
+if os.environ.get("MPN_TRACE_PER_CTA"):
+    # per-CTA view of the last launch: when did every CTA's fc1 accumulators complete / its partial sums leave / its fc2
+    # accumulators complete (us after the first prologue stamp), in blockIdx order -- is the spread systematic?
+    t = det.fused_trace(True).astype(np.int64)
+    t0 = t[:, 0].min()
+    smid = t[:, 13] if t.shape[1] > 13 else None
+    print("cta hq z   fc1_done  partials_out  fc2_done")
+    for cta in range(t.shape[0]):
+        row = [(t[cta, k] - t0) / 1e3 if t[cta, k] > 0 else float("nan") for k in (3, 4, 9)]
+        print(f"{cta:3d} {cta % 4:2d} {cta // 4:2d}  {row[0]:8.2f}  {row[1]:8.2f}  {row[2]:8.2f}")
 det.fused_trace(False)
 det.close()
