@@ -254,6 +254,11 @@ MPN_API int mpn_debug_skip(mpn_handle *h, uint32_t mask);
  * 8 y1 slice stored, 6 producer past barrier 2, 9 fc2 accumulators complete, 10 logits stored.  Synchronises the device. */
 MPN_API int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity, int32_t *grid_out);
 
+/* Development aid: globaltimer stamps (ns) of the sort / NMS kernel of the most recent call, 16 slots per image: 0 CTA
+ * resident, 1 candidate scan complete, 2 keys sorted, 3 first chunk decoded, 4 all chunks resolved, 5 results published,
+ * 6 person list built (the last CTA only).  Synchronises the device.                                         */
+MPN_API int mpn_debug_nms_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity);
+
 /* Counters of the most recent run (valid after the stream has been synchronised): number of kernels launched by the
  * last mpn_run / stage call, and the sum over calls since creation.                                       */
 MPN_API int mpn_launch_count(const mpn_handle *h, int64_t *last_call, int64_t *total);

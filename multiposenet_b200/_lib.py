@@ -99,6 +99,7 @@ SYMBOLS = {
     "mpn_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "mpn_get_profile": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "mpn_debug_fused_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),
+    "mpn_debug_nms_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
     "mpn_debug_skip": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mpn_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

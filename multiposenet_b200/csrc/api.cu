@@ -205,6 +205,7 @@ int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *b
     a.person_img = h->person_img;
     a.person_offsets = h->person_offsets;
     a.person_offsets_out = offsets_out;
+    a.trace = h->nms_trace;
     return launched(h, launch_detect(t, a, s, after_candidates), first, "detect");
 }
 
@@ -435,7 +436,7 @@ void mpn_destroy(mpn_handle *h)
     prn_fused_release(h);
     prn_big_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
-                    h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_partial2, h->hm_counter, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
+                    h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_partial2, h->hm_counter, h->nms_trace, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1118,6 +1119,28 @@ int mpn_test_sigmoid_monotone(mpn_handle *h, uint32_t key_begin, uint64_t count,
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     return launched(h, launch_test_monotone(key_begin, count, reinterpret_cast<unsigned long long *>(violations),
                                             (cudaStream_t)stream), true, "test sigmoid monotone");
+}
+
+int mpn_debug_nms_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity)
+{
+    if (!h) return MPN_ERR_INVALID_ARGUMENT;
+    MPN_CUDA(h, cudaSetDevice(h->cfg.device));
+    MPN_CUDA(h, cudaDeviceSynchronize());
+    // the trace pointer is a kernel argument baked into the captured graphs: drop them whenever tracing is switched
+    for (GraphEntry &e : h->graphs)
+        if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
+    h->graph_miss_streak = 0;
+    const size_t n = (size_t)h->cfg.max_batch * 16;
+    if (enable && !h->nms_trace) {
+        MPN_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->nms_trace), n * sizeof(unsigned long long)));
+        MPN_CUDA(h, cudaMemset(h->nms_trace, 0, n * sizeof(unsigned long long)));
+    }
+    if (host_out && h->nms_trace) {
+        const size_t m = (size_t)capacity < n ? (size_t)capacity : n;
+        MPN_CUDA(h, cudaMemcpy(host_out, h->nms_trace, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (!enable && h->nms_trace) { cudaFree(h->nms_trace); h->nms_trace = nullptr; }
+    return MPN_OK;
 }
 
 int mpn_debug_skip(mpn_handle *h, uint32_t mask)

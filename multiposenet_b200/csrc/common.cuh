@@ -59,6 +59,7 @@ struct DetectArgs {
     int *person_img;         // [B*max_det]
     int *person_offsets;     // [B+1]
     int *person_offsets_out; // user copy [B+1] or NULL
+    unsigned long long *trace;   // optional [B, 16] globaltimer stamps of the sort / NMS phases (mpn_debug_nms_trace)
 };
 
 // Optional per-kernel timing (mpn_set_profiling): every launcher marks the stream before each kernel it launches.

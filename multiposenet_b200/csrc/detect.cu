@@ -217,6 +217,15 @@ struct NmsSmem {
     int n_kept;                                // boxes kept by the current chunk
 };
 
+__device__ __forceinline__ void nms_stamp(const DetectArgs &a, int slot)
+{
+    if (a.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
 {
@@ -225,7 +234,9 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
     NmsSmem<T> &sm = *reinterpret_cast<NmsSmem<T> *>(smem_raw);
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
+    nms_stamp(a, 0);                                   // CTA resident
     pdl_wait();                                        // the candidate scan has completed
+    nms_stamp(a, 1);                                   // candidates complete
     const int C = min(a.cand_count[img], a.key_cap);
     unsigned long long *gkeys = a.cand_keys + (size_t)img * a.key_cap;
     const unsigned long long *keys;
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
         keys = work;
     }
     __syncthreads();
+    nms_stamp(a, 2);                                   // keys sorted
 
     float *boxes_out = a.boxes + (size_t)img * a.max_det * 4;
     float *scores_out = a.scores + (size_t)img * a.max_det;
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
             for (int j = 0; j < kept; ++j)
                 if (nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr) { alive = false; break; }
         }
+        if (base == 0) nms_stamp(a, 3);                // first chunk decoded and tested against the kept boxes
         const int n_warps = (n + 31) >> 5;             // warps that hold candidates of this chunk
         if (warp >= n_warps && lane == 0) { sm.alive[0][warp] = 0u; sm.alive[1][warp] = 0u; }
         __syncthreads();                               // sm.box complete, idle warps' ballots zeroed
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
         kept += nk;
         __syncthreads();
     }
+    nms_stamp(a, 4);                                   // all chunks resolved
     // zero padding (detector/utils/nms.py:47-52)
     for (int k = kept + tid; k < a.max_det; k += kNmsThreads) {
         reinterpret_cast<float4 *>(boxes_out)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -365,10 +379,13 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
         __syncthreads();
         if (tid == 0) sm.n_kept = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1u);
         __syncthreads();
+        nms_stamp(a, 5);                               // this image's results published, arrival counted
         if (sm.n_kept) {
             __threadfence();                           // ... and so are everybody else's
             if (tid == 0) *a.done_counter = 0u;        // re-armed for the next call
             person_list(a, reinterpret_cast<int *>(sm.keys));
+            __syncthreads();
+            nms_stamp(a, 6);                           // person list built (last CTA only)
         }
     }
 }

@@ -55,6 +55,7 @@ struct mpn_handle {
     float *person_box;
     int *person_img;
     int *person_offsets;
+    unsigned long long *nms_trace;   // mpn_debug_nms_trace (NULL: off)
     // heatmap workspace
     float *kh_ws;
     float *nh_ws;           // normalised heatmaps (create_pb.py:93-94), never returned

@@ -711,6 +711,123 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
     }
 }
 
+// The same op on the UN-padded keypoint_heatmaps [.., 17] with the min-max normalisation of create_pb.py:93-94 applied to
+// every tap (the path of mpn_run for large maps with few persons, where a pass over the whole map to normalise it would
+// cost more than it saves), compiled for the reference's crop size like crop_padded_kernel: one person per blockIdx.x, a
+// band of ROWS crop rows per blockIdx.y, a thread owns one (crop column, channel) -- 36 x 17 = 612 of the CTA's 640
+// threads -- keeps its column's two source offsets, its lerp weight and its channel's normalisation constants in
+// registers and walks the rows: four scalar tap loads (the 17 lanes of a pixel read one 68-byte run), four tap
+// normalisations, three lerps, one conflict-free shared-memory store; the band then leaves as 16- / 8-byte vectors.
+// minmax == NULL: plain crop_and_resize.
+template <int CH, int CW, int ROWS>
+__global__ void __launch_bounds__((CW * kNK + 31) / 32 * 32)
+crop_tap_kernel(const float *__restrict__ src, const float *__restrict__ minmax, const int hh, const int ww,
+                const float *__restrict__ boxes, const int *__restrict__ box_ind, const int *__restrict__ n_dev,
+                const int n_host, float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
+{
+    constexpr int kThreads = (CW * kNK + 31) / 32 * 32;
+    constexpr int kPix = ROWS * CW, kOut4 = kPix * kNK / 4;
+    static_assert(CH % ROWS == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
+    __shared__ AxisTab s_y[ROWS];                      // lo / hi: element offsets of the two source rows (row * ww * 17)
+    __shared__ __align__(16) float s_out[kPix * kNK];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const float4 box = __ldcg(reinterpret_cast<const float4 *>(boxes) + n);
+    const int b_raw = __ldcg(box_ind + n);
+    const int N = n_dev ? __ldcg(n_dev) : n_host;
+    if (n >= N) return;
+    const int b = b_raw;
+    const int cy0 = blockIdx.y * ROWS;
+    const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
+    if (tid < ROWS) {
+        const float y1 = box.x, y2 = box.z;
+        float in_y;
+        if (CH > 1) {
+            const float hs = fdiv(fmul(fsub(y2, y1), hm1), (float)(CH - 1));
+            in_y = fadd(fmul(y1, hm1), fmul((float)(cy0 + tid), hs));
+        } else {
+            in_y = fmul(fmul(0.5f, fadd(y1, y2)), hm1);
+        }
+        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+        AxisTab t;
+        t.valid = !(in_y < 0.0f || in_y > hm1) ? 1u : 0u;
+        t.lo = t.valid ? (unsigned)(top * ww * kNK) : 0u; t.hi = t.valid ? (unsigned)(bot * ww * kNK) : 0u;
+        t.w = fsub(in_y, (float)top);
+        s_y[tid] = t;
+    }
+    const int cx = min(tid / kNK, CW - 1), c = tid - (tid / kNK) * kNK;
+    const bool owner = tid < CW * kNK;
+    float in_x;
+    {
+        const float x1 = box.y, x2 = box.w;
+        if (CW > 1) {
+            const float ws = fdiv(fmul(fsub(x2, x1), wm1), (float)(CW - 1));
+            in_x = fadd(fmul(x1, wm1), fmul((float)cx, ws));
+        } else {
+            in_x = fmul(fmul(0.5f, fadd(x1, x2)), wm1);
+        }
+    }
+    const bool x_valid = !(in_x < 0.0f || in_x > wm1);
+    const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
+    const float lx = fsub(in_x, (float)left);
+    const float *img = src + (size_t)b * hh * ww * kNK;
+    unsigned xl = x_valid ? (unsigned)(left * kNK + c) : 0u, xr = x_valid ? (unsigned)(right * kNK + c) : 0u;
+    asm volatile("" : "+r"(xl), "+r"(xr));
+    // this thread's channel (create_pb.py:90-94)
+    const bool norm = minmax != nullptr;
+    float m = 0.0f, d = 1.0f, rcp = 1.0f, mask = 1.0f;
+    if (norm) {
+        m = __ldg(minmax + ((size_t)b * kNK + c) * 2);
+        const float hi = __ldg(minmax + ((size_t)b * kNK + c) * 2 + 1);
+        d = fsub(hi, m);
+        rcp = range_rcp(d);
+        mask = hi > 0.2f ? 1.0f : 0.0f;
+    }
+    const bool careful = rcp == 0.0f || m < 1e-22f;    // see heatmap_norm_kernel
+    auto tap = [&](unsigned off) {
+        const float v = __ldg(img + off);
+        if (!norm) return v;
+        if (careful) return normalise_tap(v, m, d, rcp, mask);
+        const float a = fsub(v, m), q0 = fmul(a, rcp);
+        return fmul(__fmaf_rn(__fmaf_rn(-q0, d, a), rcp, q0), mask);
+    };
+    __syncthreads();
+    if (owner) {
+        float *so = s_out + tid;                       // cx * 17 + c
+#pragma unroll 4                    // four rows' taps (16 loads) in flight
+        for (int r = 0; r < ROWS; ++r) {
+            const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
+            float o = 0.0f;
+            if (ty.w != 0u && x_valid) {
+                const float ly = __uint_as_float(ty.z);
+                const float tl = tap(ty.x + xl), tr = tap(ty.x + xr), bl = tap(ty.y + xl), br = tap(ty.y + xr);
+                const float tpv = fadd(tl, fmul(fsub(tr, tl), lx));
+                const float btv = fadd(bl, fmul(fsub(br, bl), lx));
+                o = fadd(tpv, fmul(fsub(btv, tpv), ly));
+            }
+            so[r * (CW * kNK)] = o;
+        }
+    }
+    __syncthreads();
+    const size_t o0 = ((size_t)n * CH + cy0) * (CW * kNK);
+#pragma unroll
+    for (int it = 0; it < (kOut4 + kThreads - 1) / kThreads; ++it) {
+        const int f = it * kThreads + tid;
+        if (f < kOut4) {
+            const float4 v = reinterpret_cast<const float4 *>(s_out)[f];
+            if (out_f32) __stcs(reinterpret_cast<float4 *>(out_f32 + o0) + f, v);
+            if (out_bf16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u;
+                u.x = *reinterpret_cast<const unsigned *>(&lo);
+                u.y = *reinterpret_cast<const unsigned *>(&hi);
+                __stcs(reinterpret_cast<uint2 *>(out_bf16 + o0) + f, u);
+            }
+        }
+    }
+}
+
 // inference/utils.py:29-52.  One CTA of 17 x 32 threads: thread (c, q) scans positions q, q+32, ...
 __global__ void __launch_bounds__(kNK * 32) get_keypoints_kernel(const float *__restrict__ hm, const int hh,
                                                                 const int ww, const double ymin, const double xmin,
@@ -866,6 +983,12 @@ int launch_crop(const float *src, const float *minmax, int hh, int ww, const flo
                 __nv_bfloat16 *crops_bf16, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
+    if (crop_h == 56 && crop_w == 36) {                // the reference's crop size (create_pb.py:19): the specialised kernel
+        prof_mark(s, "crop");
+        launch_k(crop_tap_kernel<56, 36, 8>, dim3(n_max, 7), dim3((36 * kNK + 31) / 32 * 32), 0, s, true, src, minmax, hh, ww, boxes,
+                 box_ind, n_dev, n_host, crops_f32, crops_bf16);
+        return 1;
+    }
     int bands = kCropBands;
     while (((crop_h + bands - 1) / bands) * crop_w > kCropMaxPix) ++bands;
     // every band must start at a multiple of 4 samples: rows_per_band * crop_w * 17 % 4 == 0

@@ -527,6 +527,13 @@ class Detector:
         self._check(self._lib.mpn_debug_fused_trace(self._handle, 1 if enable else 0, buf, cap, C.byref(g)))
         return np.frombuffer(buf, dtype=np.uint64, count=g.value * 16).reshape(g.value, 16).copy()
 
+    def nms_trace(self, enable=True):
+        """Development aid (mpn_debug_nms_trace): numpy uint64 [max_batch, 16] of per-image phase timestamps in ns."""
+        n = self.config.max_batch * 16
+        buf = (C.c_uint64 * n)()
+        self._check(self._lib.mpn_debug_nms_trace(self._handle, 1 if enable else 0, buf, n))
+        return np.frombuffer(buf, dtype=np.uint64, count=n).reshape(-1, 16).copy()
+
     def debug_skip(self, mask):
         """Development aid (mpn_debug_skip): do not launch the stages whose bit is set (1 detect, 2 heatmap stage, 8 crop,
         16 PRN, 32 keypoint decode); their outputs keep the previous call's values."""

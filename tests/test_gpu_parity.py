@@ -284,6 +284,27 @@ def test_crop_weak_channel_is_zeroed_and_identity_box(det6):
     assert_bit_equal(plain[0], kh[0], "box [0,0,1,1] on a 56x36 map is the identity")
 
 
+def test_crop_other_crop_sizes_take_the_general_kernel():
+    """The specialised crop kernels are compiled for the reference's 56 x 36 crop (create_pb.py:19); a handle configured
+    with another crop size takes the runtime-sized kernel: same op, same bits."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    wl = synthetic.WORKLOADS["tiny"]
+    inp = synthetic.make_inputs(wl)
+    kh, _, mn, mx = oracle.heatmaps(inp["heatmap_logits"])
+    rng = np.random.default_rng(8)
+    boxes = np.concatenate([inp["gt_boxes"][0], np.array([[0, 0, 1, 1], [-0.2, -0.1, 0.5, 0.6], [0.9, 0.9, 0.1, 0.1]], np.float32),
+                            rng.uniform(0, 1, (5, 4)).astype(np.float32)]).astype(np.float32)
+    ind = rng.integers(0, 2, len(boxes)).astype(np.int32)
+    for size in ((8, 16), (24, 12)):
+        det = Detector(None, DetectorConfig(max_batch=2, max_height=256, max_width=256, crop_size=size))
+        try:
+            got = det.crop(_cuda(kh), _cuda(boxes), _cuda(ind), _cuda(np.stack([mn, mx], -1))).cpu().numpy()
+            assert got.shape == (len(boxes),) + size + (17,)
+            assert_bit_equal(got, oracle.crop_and_resize(kh, boxes, ind, size, mn, mx), f"crop size {size}")
+        finally:
+            det.close()
+
+
 # ----------------------------------------------------------------------------------------------- PRN
 def _rel_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
