@@ -462,13 +462,7 @@ struct __align__(16) AxisTab {
     unsigned valid;                   // 0: outside the source map (extrapolation value 0)
 };
 
-// CACHE (large calls): the op's horizontal lerps tl + (tr - tl) lx of a source row do not depend on the crop row that
-// uses them, and consecutive crop rows share source rows (all of them whenever the box is less than twice as tall in
-// source pixels as the crop: a thread's last two horizontally interpolated rows stay in registers and are reused when
-// the next crop row asks for the same source row (the row ids come from the shared table: the test is uniform over the
-// CTA).  Same operations on the same operands, so the same bits, at half to a third of the tap loads -- the kernel is bound
-// by L1 wavefronts.  Small calls (latency, not throughput) keep all taps of a thread in flight instead (CACHE = false).
-template <int CH, int CW, int ROWS, bool CACHE>
+template <int CH, int CW, int ROWS>
 __global__ void __launch_bounds__((CW * kGroups + 31) / 32 * 32)
 crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, const float *__restrict__ boxes,
                    const int *__restrict__ box_ind, const int *__restrict__ n_dev, const int n_host,
@@ -476,7 +470,7 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
 {
     constexpr int kThreads = (CW * kGroups + 31) / 32 * 32;          // 192 for 36 columns: 180 of them own a (column, group)
     constexpr int kPix = ROWS * CW, kOut4 = kPix * kNK / 4;
-    static_assert(CH % ROWS == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
+    static_assert(CH % ROWS == 0 && ROWS % 4 == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
     __shared__ AxisTab s_y[ROWS];
     __shared__ __align__(16) float s_out[kPix * kNK];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -528,57 +522,38 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
     __syncthreads();
     if (owner) {
         float *so = s_out + cx * kNK + 4 * g;
-        float held[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};      // CACHE: the last top / bottom source rows
-        unsigned held_row[2] = {0xffffffffu, 0xffffffffu};
-        // one source row, horizontally interpolated at this thread's column: tl + (tr - tl) * lx per channel
-        auto hrow = [&](unsigned row, float (&h)[4]) {
-            const float4 a = __ldg(img + (row + xl)), bq = __ldg(img + (row + xr));
-            const float l[4] = {a.x, a.y, a.z, a.w}, rr[4] = {bq.x, bq.y, bq.z, bq.w};
+        // Four crop rows at a time: ALL sixteen tap loads are issued before the first lerp (rows or columns outside the map
+        // carry offset 0: the load is harmless and its result unused).  What the kernel needs is loads in flight: a variant
+        // that reused horizontally interpolated source rows across crop rows (a third of the loads, same bits) was 20 %
+        // SLOWER at 2 805 persons, because its loads sat behind row-dependent branches, two at a time.
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = fadd(l[k], fmul(fsub(rr[k], l[k]), lx));
-        };
-#pragma unroll 4                    // CACHE = false: four rows' taps (16 loads) in flight
-        for (int r = 0; r < ROWS; ++r) {
-            const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
-            float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (ty.w != 0u && x_valid) {
-                const float ly = __uint_as_float(ty.z);
-                float tp[4], bt[4];
-                if (CACHE) {
-                    if (ty.x == held_row[0]) {
+        for (int r0 = 0; r0 < ROWS; r0 += 4) {
+            uint4 ty[4];
+            float4 tap[4][4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) tp[k] = held[0][k];
-                    } else if (ty.x == held_row[1]) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) tp[k] = held[1][k];
-                    } else {
-                        hrow(ty.x, tp);
-                    }
-                    if (ty.y == ty.x) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) bt[k] = tp[k];
-                    } else if (ty.y == held_row[1]) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) bt[k] = held[1][k];
-                    } else if (ty.y == held_row[0]) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) bt[k] = held[0][k];
-                    } else {
-                        hrow(ty.y, bt);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { held[0][k] = tp[k]; held[1][k] = bt[k]; }
-                    held_row[0] = ty.x; held_row[1] = ty.y;
-                } else {
-                    hrow(ty.x, tp);
-                    hrow(ty.y, bt);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) o[k] = fadd(tp[k], fmul(fsub(bt[k], tp[k]), ly));
+            for (int i = 0; i < 4; ++i) {
+                ty[i] = *reinterpret_cast<const uint4 *>(&s_y[r0 + i]);
+                tap[i][0] = __ldg(img + (ty[i].x + xl)); tap[i][1] = __ldg(img + (ty[i].x + xr));
+                tap[i][2] = __ldg(img + (ty[i].y + xl)); tap[i][3] = __ldg(img + (ty[i].y + xr));
             }
-            so[r * (CW * kNK)] = o[0];
-            if (g < kGroups - 1) {                     // group 4 holds channel 16 only
-                so[r * (CW * kNK) + 1] = o[1]; so[r * (CW * kNK) + 2] = o[2]; so[r * (CW * kNK) + 3] = o[3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ly = __uint_as_float(ty[i].z);
+                const float tl[4] = {tap[i][0].x, tap[i][0].y, tap[i][0].z, tap[i][0].w};
+                const float tr[4] = {tap[i][1].x, tap[i][1].y, tap[i][1].z, tap[i][1].w};
+                const float bl[4] = {tap[i][2].x, tap[i][2].y, tap[i][2].z, tap[i][2].w};
+                const float br[4] = {tap[i][3].x, tap[i][3].y, tap[i][3].z, tap[i][3].w};
+                const bool inside = ty[i].w != 0u && x_valid;
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float tpv = fadd(tl[k], fmul(fsub(tr[k], tl[k]), lx));
+                    const float btv = fadd(bl[k], fmul(fsub(br[k], bl[k]), lx));
+                    o[k] = inside ? fadd(tpv, fmul(fsub(btv, tpv), ly)) : 0.0f;
+                }
+                float *sr = so + (r0 + i) * (CW * kNK);
+                sr[0] = o[0];
+                if (g < kGroups - 1) { sr[1] = o[1]; sr[2] = o[2]; sr[3] = o[3]; }      // group 4 holds channel 16 only
             }
         }
     }
@@ -727,7 +702,7 @@ crop_tap_kernel(const float *__restrict__ src, const float *__restrict__ minmax,
 {
     constexpr int kThreads = (CW * kNK + 31) / 32 * 32;
     constexpr int kPix = ROWS * CW, kOut4 = kPix * kNK / 4;
-    static_assert(CH % ROWS == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
+    static_assert(CH % ROWS == 0 && ROWS % 4 == 0 && (kPix * kNK) % 4 == 0 && (CH * CW * kNK) % 4 == 0 && ROWS <= 32, "band geometry");
     __shared__ AxisTab s_y[ROWS];                      // lo / hi: element offsets of the two source rows (row * ww * 17)
     __shared__ __align__(16) float s_out[kPix * kNK];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -785,8 +760,7 @@ crop_tap_kernel(const float *__restrict__ src, const float *__restrict__ minmax,
         mask = hi > 0.2f ? 1.0f : 0.0f;
     }
     const bool careful = rcp == 0.0f || m < 1e-22f;    // see heatmap_norm_kernel
-    auto tap = [&](unsigned off) {
-        const float v = __ldg(img + off);
+    auto normalised = [&](float v) {                   // create_pb.py:93-94 on one tap
         if (!norm) return v;
         if (careful) return normalise_tap(v, m, d, rcp, mask);
         const float a = fsub(v, m), q0 = fmul(a, rcp);
@@ -795,18 +769,27 @@ crop_tap_kernel(const float *__restrict__ src, const float *__restrict__ minmax,
     __syncthreads();
     if (owner) {
         float *so = s_out + tid;                       // cx * 17 + c
-#pragma unroll 4                    // four rows' taps (16 loads) in flight
-        for (int r = 0; r < ROWS; ++r) {
-            const uint4 ty = *reinterpret_cast<const uint4 *>(&s_y[r]);
-            float o = 0.0f;
-            if (ty.w != 0u && x_valid) {
-                const float ly = __uint_as_float(ty.z);
-                const float tl = tap(ty.x + xl), tr = tap(ty.x + xr), bl = tap(ty.y + xl), br = tap(ty.y + xr);
+        // four crop rows at a time, all sixteen tap loads issued before the first use (rows or columns outside the map
+        // carry offset 0: the load is harmless and its result unused)
+#pragma unroll
+        for (int r0 = 0; r0 < ROWS; r0 += 4) {
+            uint4 ty[4];
+            float raw[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ty[i] = *reinterpret_cast<const uint4 *>(&s_y[r0 + i]);
+                raw[i][0] = __ldg(img + (ty[i].x + xl)); raw[i][1] = __ldg(img + (ty[i].x + xr));
+                raw[i][2] = __ldg(img + (ty[i].y + xl)); raw[i][3] = __ldg(img + (ty[i].y + xr));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ly = __uint_as_float(ty[i].z);
+                const float tl = normalised(raw[i][0]), tr = normalised(raw[i][1]);
+                const float bl = normalised(raw[i][2]), br = normalised(raw[i][3]);
                 const float tpv = fadd(tl, fmul(fsub(tr, tl), lx));
                 const float btv = fadd(bl, fmul(fsub(br, bl), lx));
-                o = fadd(tpv, fmul(fsub(btv, tpv), ly));
+                so[(r0 + i) * (CW * kNK)] = (ty[i].w != 0u && x_valid) ? fadd(tpv, fmul(fsub(btv, tpv), ly)) : 0.0f;
             }
-            so[r * (CW * kNK)] = o;
         }
     }
     __syncthreads();
@@ -1010,17 +993,16 @@ int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, cons
 {
     if (n_max <= 0) return 0;
     if (!crop_padded_supported(crop_h, crop_w)) return -(int)cudaErrorInvalidValue;
-    // Rows per CTA: 4 (all of a thread's taps in flight at once, twice the CTAs) while the call is small enough to be a
-    // latency problem -- at most one resident wave of CTAs -- 8 with the source-row cache (half the per-CTA prologue per
-    // value, a third to a half of the tap loads) beyond.
+    // Rows per CTA: 4 (twice the CTAs) while the call is small enough to be a latency problem -- at most one resident wave of
+    // CTAs -- 8 (half the per-CTA prologue per value) beyond.
     prof_mark(s, "crop");
     const dim3 block((36 * kGroups + 31) / 32 * 32);
     if (n_max <= 640)
-        launch_k(crop_padded_kernel<56, 36, 4, false>, dim3(n_max, 14), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev,
-                 n_host, crops_f32, crops_bf16);
+        launch_k(crop_padded_kernel<56, 36, 4>, dim3(n_max, 14), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
+                 crops_f32, crops_bf16);
     else
-        launch_k(crop_padded_kernel<56, 36, 8, true>, dim3(n_max, 7), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev,
-                 n_host, crops_f32, crops_bf16);
+        launch_k(crop_padded_kernel<56, 36, 8>, dim3(n_max, 7), block, 0, s, true, nh, hh, ww, boxes, box_ind, n_dev, n_host,
+                 crops_f32, crops_bf16);
     return 1;
 }
 
