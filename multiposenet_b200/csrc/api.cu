@@ -157,8 +157,7 @@ struct ProfScope {
 };
 
 int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *boxes, float *scores, int *num_boxes,
-              int *sel_anchor, int *n_candidates, int *offsets_out, cudaStream_t s, bool first,
-              cudaEvent_t after_candidates = nullptr)
+              int *sel_anchor, int *n_candidates, cudaStream_t s, bool first, cudaEvent_t after_candidates = nullptr)
 {
     int rc = check_image_size(h, in->batch, in->height, in->width);
     if (rc) return rc;
@@ -195,16 +194,11 @@ int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *b
     a.cand_keys = h->cand_keys;
     a.key_cap = h->key_cap;
     a.cand_count = h->cand_count;
-    a.done_counter = h->done_counter;
     a.boxes = boxes;
     a.scores = scores;
     a.num_boxes = num_boxes;
     a.sel_anchor = sel_anchor;
     a.n_candidates = n_candidates;
-    a.person_box = h->person_box;
-    a.person_img = h->person_img;
-    a.person_offsets = h->person_offsets;
-    a.person_offsets_out = offsets_out;
     a.trace = h->nms_trace;
     return launched(h, launch_detect(t, a, s, after_candidates), first, "detect");
 }
@@ -332,7 +326,6 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
 
     MPN_ALLOC(h->cand_keys, B * h->key_cap);
     MPN_ALLOC(h->cand_count, B);
-    MPN_ALLOC(h->done_counter, 1);
     MPN_ALLOC(h->person_box, NP * 4);
     MPN_ALLOC(h->person_img, NP);
     MPN_ALLOC(h->person_offsets, B + 1);
@@ -369,7 +362,6 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
         cudaMemset(h->prn_ws.y1_bf16, 0, NPpad * Hd * sizeof(__nv_bfloat16));
     }
     h->prn_ws.n_max = (int)NPpad;
-    cudaMemset(h->done_counter, 0, sizeof(unsigned int));
     cudaMemset(h->cand_count, 0, B * sizeof(int));
     cudaMemset(h->person_offsets, 0, (B + 1) * sizeof(int));
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
@@ -435,7 +427,7 @@ void mpn_destroy(mpn_handle *h)
     prn_bf16_release(h);
     prn_fused_release(h);
     prn_big_release(h);
-    void *ptrs[] = {h->cand_keys, h->cand_count, h->done_counter, h->person_box, h->person_img, h->person_offsets,
+    void *ptrs[] = {h->cand_keys, h->cand_count, h->person_box, h->person_img, h->person_offsets,
                     h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_partial2, h->hm_counter, h->nms_trace, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
                     h->W2t, h->prn_ws.partial, h->prn_ws.y1, h->prn_ws.y1_bf16};
     for (void *p : ptrs)
@@ -517,7 +509,7 @@ int mpn_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *
     if (!h) return MPN_ERR_INVALID_ARGUMENT;
     if (!in) return fail(h, MPN_ERR_INVALID_ARGUMENT, "inputs is NULL");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
-    return do_detect(h, in, p, boxes, scores, num_boxes, sel_anchor, n_candidates, nullptr, (cudaStream_t)stream, true);
+    return do_detect(h, in, p, boxes, scores, num_boxes, sel_anchor, n_candidates, (cudaStream_t)stream, true);
 }
 
 int mpn_heatmaps(mpn_handle *h, const float *heatmap_logits, int32_t batch, int32_t hm_height, int32_t hm_width,
@@ -574,9 +566,12 @@ int mpn_crop_padded(mpn_handle *h, const float *normalised, int32_t batch, int32
         return fail(h, MPN_ERR_UNSUPPORTED, "the padded crop kernel does not cover this crop size");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
     if (n == 0) { h->last_launches = 0; return MPN_OK; }
-    return launched(h, launch_crop_padded(normalised, hm_height, hm_width, boxes, box_ind, nullptr, n, n, h->cfg.crop_height,
-                                          h->cfg.crop_width, crops_f32, reinterpret_cast<__nv_bfloat16 *>(crops_bf16),
-                                          (cudaStream_t)stream), true, "crop (padded)");
+    PersonList pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.boxes = boxes; pl.box_ind = box_ind; pl.n_host = n;
+    return launched(h, launch_crop_padded(normalised, hm_height, hm_width, pl, n, h->cfg.crop_height, h->cfg.crop_width,
+                                          crops_f32, reinterpret_cast<__nv_bfloat16 *>(crops_bf16), (cudaStream_t)stream), true,
+                    "crop (padded)");
 }
 
 int mpn_heatmap_head(mpn_handle *h, const float *features, const float *weight, const float *bias, int32_t batch,
@@ -603,8 +598,12 @@ int mpn_crop(mpn_handle *h, const float *keypoint_heatmaps, const float *minmax,
     if (!keypoint_heatmaps || !boxes || !box_ind || !crops) return fail(h, MPN_ERR_INVALID_ARGUMENT, "pointer is NULL");
     if (n < 0 || batch < 1 || hm_height < 1 || hm_width < 1) return fail(h, MPN_ERR_INVALID_ARGUMENT, "bad sizes");
     MPN_CUDA(h, cudaSetDevice(h->cfg.device));
-    return launched(h, launch_crop(keypoint_heatmaps, minmax, hm_height, hm_width, boxes, box_ind, nullptr, n, n,
-                                   h->cfg.crop_height, h->cfg.crop_width, crops, nullptr, (cudaStream_t)stream), true, "crop");
+    if (n == 0) { h->last_launches = 0; return MPN_OK; }
+    PersonList pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.boxes = boxes; pl.box_ind = box_ind; pl.n_host = n;
+    return launched(h, launch_crop(keypoint_heatmaps, minmax, hm_height, hm_width, pl, n, h->cfg.crop_height, h->cfg.crop_width,
+                                   crops, nullptr, (cudaStream_t)stream), true, "crop");
 }
 
 int mpn_prn(mpn_handle *h, const float *crops, int32_t n, int32_t prn_mode, float *logits, void *stream)
@@ -708,8 +707,8 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     // heatmap CTAs fill the other SMs.  Released together with the candidate scan they would occupy every SM for their
     // whole life and sort/NMS would start only when they drain (measured: no overlap at all).
     if (!(skip & 1u))
-        rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, out->person_offsets, sd,
-                       !(padded && !(skip & 2u)), fork ? h->ev_cand : nullptr);
+        rc = do_detect(h, in, p, out->boxes, out->scores, out->num_boxes, nullptr, nullptr, sd, !(padded && !(skip & 2u)),
+                       fork ? h->ev_cand : nullptr);
     if (rc) return rc;
     if (fork) {
         MPN_CUDA(h, cudaEventRecord(h->ev_join, sd));
@@ -730,13 +729,17 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     const int n_max = in->batch * p->max_detections;
     const int *n_dev = h->person_offsets + in->batch;
     const bool bf16 = p->prn_mode == MPN_PRN_BF16;
+    // every crop CTA derives its person from num_boxes / boxes (create_pb.py:96-103); one CTA writes the flat list
+    PersonList pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.num_boxes = out->num_boxes; pl.det_boxes = out->boxes; pl.B = in->batch; pl.max_det = p->max_detections;
+    pl.person_box = h->person_box; pl.person_img = h->person_img; pl.person_offsets = h->person_offsets;
+    pl.person_offsets_out = out->person_offsets;
     if (!(skip & 8u))
-        rc = launched(h, padded ? launch_crop_padded(h->nh_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
-                                                     h->cfg.crop_height, h->cfg.crop_width, h->crops_f32,
-                                                     bf16 ? h->crops_bf16 : nullptr, s)
-                                : launch_crop(kh, h->minmax_ws, hh, ww, h->person_box, h->person_img, n_dev, 0, n_max,
-                                              h->cfg.crop_height, h->cfg.crop_width, h->crops_f32,
-                                              bf16 ? h->crops_bf16 : nullptr, s),
+        rc = launched(h, padded ? launch_crop_padded(h->nh_ws, hh, ww, pl, n_max, h->cfg.crop_height, h->cfg.crop_width,
+                                                     h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s)
+                                : launch_crop(kh, h->minmax_ws, hh, ww, pl, n_max, h->cfg.crop_height, h->cfg.crop_width,
+                                              h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s),
                       false, "crop");
     if (rc) return rc;
     // 4. PRN                                                 (detector/prn.py:5-25)

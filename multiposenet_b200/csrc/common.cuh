@@ -47,19 +47,34 @@ struct DetectArgs {
     unsigned long long *cand_keys;   // [B, key_cap]
     int key_cap;                     // power of two >= A
     int *cand_count;                 // [B]
-    unsigned int *done_counter;      // [1]
     // outputs
     float *boxes;            // [B, max_det, 4]
     float *scores;           // [B, max_det]
     int *num_boxes;          // [B]
     int *sel_anchor;         // [B, max_det] or NULL
     int *n_candidates;       // [B] or NULL
-    // person list (create_pb.py:96-103)
-    float *person_box;       // [B*max_det, 4]
-    int *person_img;         // [B*max_det]
-    int *person_offsets;     // [B+1]
-    int *person_offsets_out; // user copy [B+1] or NULL
     unsigned long long *trace;   // optional [B, 16] globaltimer stamps of the sort / NMS phases (mpn_debug_nms_trace)
+};
+
+// How a crop CTA finds the person of its row n (create_pb.py:96-103: boxes = concat_i predicted_boxes[i][:num_boxes[i]],
+// box_ind likewise).  Either an explicit flat list (the stage entry points), or -- inside mpn_run -- derived by every CTA
+// from the detection outputs themselves: row n is box k of image b where the exclusive scan of num_boxes brackets n.  The
+// sort / NMS kernel therefore ends when its last image is resolved; an earlier version had its last CTA build the flat
+// list behind a fence and an atomic counter, a tail of ~4.5 us on the critical chain of every call.  One extra CTA of the
+// crop grid (blockIdx.x == 0 of the last blockIdx.y) writes the list and the offsets for whoever wants them afterwards
+// (person count for the PRN / decode kernels, person_offsets output, mpn_debug_fetch).
+struct PersonList {
+    const float *boxes;      // explicit: [N, 4]
+    const int *box_ind;      // explicit: [N]
+    const int *n_dev;        // explicit: device person count (NULL: n_host)
+    int n_host;
+    const int *num_boxes;    // derived: [B] (NULL: explicit list)
+    const float *det_boxes;  // derived: [B, max_det, 4]
+    int B, max_det;
+    float *person_box;       // outputs of the list CTA (derived mode): [B * max_det, 4], [B * max_det], [B + 1], user copy or NULL
+    int *person_img;
+    int *person_offsets;
+    int *person_offsets_out;
 };
 
 // Optional per-kernel timing (mpn_set_profiling): every launcher marks the stream before each kernel it launches.
@@ -127,11 +142,10 @@ int launch_heatmap_norm(const float *hml, int B, int hh, int ww, float *kh, floa
                         float *minmax_ws, float *nh, float *minmax_out, int slots, cudaStream_t s);
 // crop of the padded (20 floats / pixel) normalised map written by launch_heatmap_norm
 bool crop_padded_supported(int crop_h, int crop_w);
-int launch_crop_padded(const float *nh, int hh, int ww, const float *boxes, const int *box_ind, const int *n_dev, int n_host,
-                       int n_max, int crop_h, int crop_w, float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s);
-int launch_crop(const float *kh, const float *minmax, int hh, int ww, const float *boxes, const int *box_ind,
-                const int *n_dev, int n_host, int n_max, int crop_h, int crop_w, float *crops_f32,
-                __nv_bfloat16 *crops_bf16, cudaStream_t s);
+int launch_crop_padded(const float *nh, int hh, int ww, const PersonList &pl, int n_max, int crop_h, int crop_w,
+                       float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s);
+int launch_crop(const float *kh, const float *minmax, int hh, int ww, const PersonList &pl, int n_max, int crop_h, int crop_w,
+                float *crops_f32, __nv_bfloat16 *crops_bf16, cudaStream_t s);
 int launch_get_keypoints(const float *hm, int hh, int ww, double ymin, double xmin, double ymax, double xmax,
                          double threshold, int *out, cudaStream_t s);
 

@@ -6,7 +6,6 @@
 //   detector/retinanet.py:73                 scores = sigmoid(class_predictions)
 //   detector/utils/nms.py:27-53              threshold, boolean_mask, decode, clip, NonMaxSuppressionV3, gather, pad
 //   detector/utils/box_utils.py:112-139      decode
-//   create_pb.py:96-103                      flat person list (boxes, box_ind) in image order
 //
 // Kernel 1 (candidates_*): HBM-bound scan of the class logits.  A cheap conservative logit test rejects the
 //   ~99.7 % background anchors; survivors get the exact sigmoid and a strict `> thr` test and are appended to a
@@ -15,8 +14,8 @@
 // Kernel 2 (sort_nms): one CTA per image.  Bitonic sort of the keys (shared memory up to 8192 candidates, the
 //   image's global scratch above that -- exact for any candidate count), then greedy NMS in chunks of 1024
 //   candidates: every thread decodes its candidate's box (4 gathered codes + anchor from the index), tests it
-//   against the boxes kept so far, and the chunk is resolved with ballots, two barriers per kept box.  The last
-//   CTA to finish builds the flat person list.
+//   against the boxes kept so far, and the chunk is resolved with ballots, one barrier per kept box.  (The flat person
+//   list of create_pb.py:96-103 is derived from num_boxes by the crop kernel: common.cuh, PersonList.)
 #include "common.cuh"
 #include "mpn_math.cuh"
 
@@ -148,47 +147,6 @@ __device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectAr
     return make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane), __ldg(p + 3 * plane));
 }
 
-// Flat person list in image order (create_pb.py:96-103): person_offsets = exclusive scan of num_boxes, and for every
-// person row its box and image.  Run by the LAST CTA of sort_nms_kernel to finish (one launch less on the critical
-// chain of the call); s_off is that CTA's sort area, free by then.
-__device__ __forceinline__ void person_list(const DetectArgs &a, int *s_off)
-{
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 32) {
-        int running = 0;
-        for (int b0 = 0; b0 < a.B; b0 += 32) {
-            const int b = b0 + lane;
-            const int n = (b < a.B) ? __ldcg(a.num_boxes + b) : 0;
-            int incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (b < a.B) {
-                const int off = running + incl - n;
-                if (b < 1024) s_off[b] = off;
-                a.person_offsets[b] = off;
-                if (a.person_offsets_out) a.person_offsets_out[b] = off;
-            }
-            running += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) {
-            a.person_offsets[a.B] = running;
-            if (a.person_offsets_out) a.person_offsets_out[a.B] = running;
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < a.B * a.max_det; idx += blockDim.x) {
-        const int b = idx / a.max_det, k = idx - b * a.max_det;
-        if (k < __ldcg(a.num_boxes + b)) {
-            const int row = (b < 1024 ? s_off[b] : a.person_offsets[b]) + k;
-            reinterpret_cast<float4 *>(a.person_box)[row] = __ldcg(reinterpret_cast<const float4 *>(a.boxes) + idx);
-            a.person_img[row] = b;
-        }
-    }
-}
-
 // One CTA per image.
 //   1. candidate keys -> descending order (= score desc, anchor asc).  <= 1024 candidates: rank sort in shared memory
 //      (every key counts the keys above it; no barriers); more: bitonic sort, in shared memory up to 8192 keys and in the
@@ -243,7 +201,36 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
     __syncthreads();                                   // everyone has read the count ...
     if (tid == 0) a.cand_count[img] = 0;               // ... re-arm it for the next call (no reset kernel)
 
-    if (C <= kRankSortCap) {
+    if (C <= kNmsThreads / 2) {
+        // Few keys (the ordinary, uncrowded image): SEVERAL threads per key.  With Cp = C rounded up to a power of two,
+        // thread (part, i) = (tid / Cp, tid % Cp) counts the keys above key i in its 1 / parts slice of the list; the
+        // slice counts meet in a shared-memory rank (integer additions: order does not matter).  A quarter to a half of
+        // the one-thread-per-key scan, which was a quarter of this kernel's time at 230 candidates.
+        int Cp = 32;
+        while (Cp < C) Cp <<= 1;
+        const int parts = kNmsThreads / Cp;
+        for (int i = tid; i < C; i += kNmsThreads) sm.keys[i] = gkeys[i];
+        if (tid == 0 && (C & 1)) sm.keys[C] = 0ULL;    // zero pad: never greater than a real key (score bits > 0)
+        if (tid < Cp) sm.kept_local[tid] = 0;
+        __syncthreads();
+        const int i = tid & (Cp - 1), part = tid / Cp;
+        const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sm.keys);
+        const int c2 = (C + 1) >> 1;
+        const int j0 = (int)(((long long)part * c2) / parts), j1 = (int)(((long long)(part + 1) * c2) / parts);
+        const unsigned long long k0 = i < C ? sm.keys[i] : 0ULL;
+        int r0 = 0;
+        if (i < C) {
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) {
+                const ulonglong2 kj = k2[j];
+                r0 += (kj.x > k0) + (kj.y > k0);
+            }
+            atomicAdd(&sm.kept_local[i], r0);
+        }
+        __syncthreads();
+        if (tid < C) sm.sorted[sm.kept_local[tid]] = sm.keys[tid];
+        keys = sm.sorted;
+    } else if (C <= kRankSortCap) {
         for (int i = tid; i < C; i += kNmsThreads) sm.keys[i] = gkeys[i];
         if (tid == 0 && (C & 1)) sm.keys[C] = 0ULL;    // zero pad: never greater than a real key (score bits > 0)
         __syncthreads();
@@ -373,20 +360,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
     if (tid == 0) {
         a.num_boxes[img] = kept;
         if (a.n_candidates) a.n_candidates[img] = C;
-    }
-    if (a.person_box) {                                // the last CTA to get here builds the flat person list
-        __threadfence();                               // this CTA's boxes / num_boxes are visible GPU-wide ...
-        __syncthreads();
-        if (tid == 0) sm.n_kept = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1u);
-        __syncthreads();
-        nms_stamp(a, 5);                               // this image's results published, arrival counted
-        if (sm.n_kept) {
-            __threadfence();                           // ... and so are everybody else's
-            if (tid == 0) *a.done_counter = 0u;        // re-armed for the next call
-            person_list(a, reinterpret_cast<int *>(sm.keys));
-            __syncthreads();
-            nms_stamp(a, 6);                           // person list built (last CTA only)
-        }
+        nms_stamp(a, 5);                               // results published
     }
 }
 

