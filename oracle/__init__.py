@@ -5,7 +5,8 @@ tests/, bench.py's cpu_baseline / --impl reference legs and
 __graft_entry__.smoke() may import this package; the product package
 (multiposenet_b200) never does.
 
-PARITY UNPINNED: see the header of mpn_oracle.c.
+PINNING: see the header of mpn_oracle.c (reference-executed goldens pin everything but the last ulp of the TensorFlow
+library kernels, which stays "parity unpinned").
 """
 import ctypes as C
 import itertools

@@ -11,13 +11,21 @@
  * third-party dependency that is NOT under /root/reference (README.md:15 pins
  * "tensorflow 1.15"); their published algorithms are restated here.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- * for this path and cannot be executed in this environment (TensorFlow is not
- * installable).  The only reference function that runs here is
- * inference/utils.py::get_keypoints; tests/golden/get_keypoints_*.npz are its
- * outputs and pin orc_get_keypoints().  Everything else is pinned only by the
- * hand-derived known answers in tests/test_oracle_kat.py and by an
- * independent numpy restatement (oracle/spec_np.py).
+ * PINNING.  The reference ships no tests, golden vectors or fixtures for this path and cannot be executed whole in this
+ * environment (TensorFlow is not installable).  What pins this file to the reference ITSELF:
+ *   - tests/golden/graph_goldens.npz: vectors produced by importing and EXECUTING the reference's own graph code
+ *     (detector/anchor_generator.py, detector/utils/box_utils.py, detector/box_predictor.py reshape_and_concatenate,
+ *     detector/retinanet.py get_predictions, detector/utils/nms.py, detector/prn.py, create_pb.py:90-142,
+ *     inference/detector.py:49-59) under a numpy-backed TensorFlow stand-in (tests/golden/tf_numpy_shim.py, generator
+ *     tests/golden/make_graph_goldens.py).  Everything the reference spells with element-wise / shape ops -- anchors,
+ *     decode around exp, clip, thresholds, masks, gather, padding, min-max normalisation, person list, argmax -> positions,
+ *     post-filter -- is reproduced by this file BIT FOR BIT (tests/test_graph_goldens.py);
+ *   - tests/golden/get_keypoints.npz: outputs of the reference's inference/utils.py::get_keypoints (runs as is).
+ * STILL UNPINNED ("parity unpinned" in the sense of the task): the last-ulp behaviour of the TensorFlow LIBRARY kernels
+ * the reference calls (Exp, Sigmoid, Softmax, NonMaxSuppressionV3, CropAndResize, MatMul).  Their published algorithms
+ * are restated here (and handed to the stand-in when the goldens are made), anchored on the reference's call sites; the
+ * hand-derived known answers of tests/test_oracle_kat.py and the independent numpy restatement oracle/spec_np.py
+ * cross-check them, torchvision.ops.nms and grid_sample give second opinions.
  *
  * Only tests/, bench.py (cpu_baseline / --impl reference) and
  * __graft_entry__.smoke() may load this library.
