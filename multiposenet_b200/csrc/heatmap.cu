@@ -448,45 +448,41 @@ __global__ void __launch_bounds__(kHmThreads, 4) heatmap_norm_kernel(const float
 }
 
 // ---- the person of a crop CTA (common.cuh: PersonList) -------------------------------------------------------------------
-// Returns false (uniformly over the CTA) when row n is past the person count.  Derived mode: warp 0 scans num_boxes (one
-// L2 round trip), finds the image b whose row range brackets n and the box index k inside it, and hands (b, k, N) to the
-// CTA through shared memory; the box itself is a second round trip.  Contains one __syncthreads().
-__device__ __forceinline__ bool find_person(const PersonList &pl, int n, int *s_p, float4 &box, int &b)
+// Returns false (uniformly over the CTA) when the CTA has no person; otherwise the box, its image b and the output row.
+// Explicit list: CTA n crops list entry n.  Derived mode: CTA n stands for SLOT (b, k) = (n / max_det, n % max_det) of the
+// padded detection outputs; warp 0 scans num_boxes -- row = (boxes of the images before b) + k, valid when k <
+// num_boxes[b], i.e. the flat order of create_pb.py:96-103 -- while every thread already has the slot's box in flight: one
+// L2 round trip in all.  Contains one __syncthreads() in derived mode.
+__device__ __forceinline__ bool find_person(const PersonList &pl, int n, int *s_p, float4 &box, int &b, int &row)
 {
     if (pl.num_boxes == nullptr) {                     // explicit list: count, box and image index in ONE round trip
         box = __ldcg(reinterpret_cast<const float4 *>(pl.boxes) + n);
         const int b_raw = __ldcg(pl.box_ind + n);
         const int N = pl.n_dev ? __ldcg(pl.n_dev) : pl.n_host;
         b = b_raw;
+        row = n;
         return n < N;
     }
+    box = __ldcg(reinterpret_cast<const float4 *>(pl.det_boxes) + n);      // zero padding when the slot is empty
+    b = n / pl.max_det;
+    const int k = n - b * pl.max_det;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        int running = 0, fb = -1, fk = 0;
-        for (int b0 = 0; b0 < pl.B; b0 += 32) {
-            const int nb = (b0 + lane < pl.B) ? __ldcg(pl.num_boxes + b0 + lane) : 0;
-            int incl = nb;
+        int before = 0, mine = 0;
+        for (int b0 = 0; b0 <= b; b0 += 32) {
+            const int nb = (b0 + lane <= b) ? __ldcg(pl.num_boxes + b0 + lane) : 0;
+            if (b0 + lane == b) mine = nb;
+            int v = (b0 + lane < b) ? nb : 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int first = running + incl - nb;     // first row of image b0 + lane
-            const unsigned hit = __ballot_sync(0xffffffffu, n >= first && n < first + nb);
-            if (hit) {
-                const int src = __ffs(hit) - 1;
-                fb = b0 + src;
-                fk = n - __shfl_sync(0xffffffffu, first, src);
-            }
-            running += __shfl_sync(0xffffffffu, incl, 31);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            before += v;
         }
-        if (lane == 0) { s_p[0] = fb; s_p[1] = fk; s_p[2] = running; }
+        mine = __shfl_sync(0xffffffffu, mine, b & 31);
+        if (lane == 0) { s_p[0] = before + k; s_p[1] = k < mine; }
     }
     __syncthreads();
-    b = s_p[0];
-    if (n >= s_p[2] || b < 0) return false;
-    box = __ldcg(reinterpret_cast<const float4 *>(pl.det_boxes) + (size_t)b * pl.max_det + s_p[1]);
-    return true;
+    row = s_p[0];
+    return s_p[1] != 0;
 }
 
 // The list CTA of a derived-mode crop grid: person_offsets = exclusive scan of num_boxes (+ the user's copy), and for every
@@ -564,8 +560,8 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
         return;
     }
     float4 box;
-    int b;
-    if (!find_person(pl, n, s_p, box, b)) return;
+    int b, row;
+    if (!find_person(pl, n, s_p, box, b, row)) return;
     const int cy0 = blockIdx.y * ROWS;
     const float hm1 = (float)(hh - 1), wm1 = (float)(ww - 1);
     if (tid < ROWS) {                                  // the band's rows (create_pb.py:106-109, crop_and_resize_op.cc)
@@ -642,7 +638,7 @@ crop_padded_kernel(const float *__restrict__ src, const int hh, const int ww, co
         }
     }
     __syncthreads();
-    const size_t o0 = ((size_t)n * CH + cy0) * (CW * kNK);           // multiple of 4 floats
+    const size_t o0 = ((size_t)row * CH + cy0) * (CW * kNK);         // multiple of 4 floats
 #pragma unroll
     for (int it = 0; it < (kOut4 + kThreads - 1) / kThreads; ++it) {
         const int f = it * kThreads + tid;
@@ -694,8 +690,8 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
         return;
     }
     float4 box;
-    int b;
-    if (!find_person(pl, n, s_p, box, b)) return;
+    int b, row;
+    if (!find_person(pl, n, s_p, box, b, row)) return;
     const int rows_per_band = (crop_h + n_bands - 1) / n_bands;
     const int cy0 = blockIdx.y * rows_per_band, cy1 = min(crop_h, cy0 + rows_per_band);
     if (cy0 >= cy1) return;
@@ -762,7 +758,7 @@ __global__ void __launch_bounds__(256) crop_kernel(const float *__restrict__ src
             r[k] = v;
             if (++c == kNK) { c = 0; ++p; }
         }
-        const size_t o = (size_t)n * D + j_begin + jl;
+        const size_t o = (size_t)row * D + j_begin + jl;
         if (out_f32) *reinterpret_cast<float4 *>(out_f32 + o) = make_float4(r[0], r[1], r[2], r[3]);
         if (out_bf16) {
             const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
