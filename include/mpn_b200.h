@@ -250,8 +250,9 @@ MPN_API int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names,
 MPN_API int mpn_debug_skip(mpn_handle *h, uint32_t mask);
 
 /* Development aid: globaltimer stamps (ns) of the phases of the most recent single-kernel PRN launch, 16 slots per CTA:
- * 0 prologue, 1 fc1 loads issued, 2 fc1 MMAs issued, 3 fc1 accumulators complete, 4 partials stored, 5 barrier 1 passed,
- * 8 y1 slice stored, 6 producer past barrier 2, 9 fc2 accumulators complete, 10 logits stored.  Synchronises the device. */
+ * 0 prologue, 7 crops ready, 1 fc1 loads issued, 2 / 14 MMAs of fc1 wave A / B issued, 3 / 13 accumulators of the wave complete,
+ * 4 / 11 its partial sums stored, 5 / 12 every CTA's partial sums there, 8 / 15 y1 slice of the wave stored, 6 producer saw
+ * the last y1 barrier, 9 fc2 accumulators complete, 10 logits stored.  Synchronises the device.                */
 MPN_API int mpn_debug_fused_trace(mpn_handle *h, int32_t enable, uint64_t *host_out, int32_t capacity, int32_t *grid_out);
 
 /* Development aid: globaltimer stamps (ns) of the sort / NMS kernel of the most recent call, 16 slots per image: 0 CTA

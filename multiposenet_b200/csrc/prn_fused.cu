@@ -45,15 +45,25 @@ namespace {
 
 using namespace tc;
 
-#ifdef MPN_FC1_EIGHTHS
-// Variant build (tools/variants.py): fc1 on hidden EIGHTHS x 18 K splits instead of quarters x 37 -- half the partial sums
-// (6 MB out and back at 78 persons), twice the activation re-reads, 16 KB weight boxes, 4 idle CTAs in fc1.
-constexpr int kHq = 8;
-constexpr int kFc1N = 128, kFc2N = 240;
-#else
-constexpr int kHq = 4;                                   // hidden quarters of fc1
-constexpr int kFc1N = 256, kFc2N = 240;                  // weight rows per CTA tile of the two layers
+// fc1 runs in kWaves passes over the hidden dimension (MPN_FC1_WAVES, build.py).  One wave: CTA = hidden quarter x 1 of
+// 37 K splits, and the weight stream stops while the grid stores its partial sums, meets, reduces and meets again.  Two
+// waves: wave w covers hidden half w (CTA = one of its two quarters x 1 of 74 K splits), and only the epilogue warps
+// take part in the store / barrier / reduce / barrier sequence of a wave -- the producer and the MMA warp go straight
+// on to the next wave's weights (second accumulator stage in TMEM), and the first half of fc2's reduction only needs the
+// first half of y1, so the weight stream continues through both sequences.  Price: twice the partial sums.
+#ifndef MPN_FC1_WAVES
+#define MPN_FC1_WAVES 1
 #endif
+constexpr int kWaves = MPN_FC1_WAVES;
+static_assert(kWaves == 1 || kWaves == 2, "fc1 waves");
+constexpr int kHq = 4;                                   // hidden quarters of fc1
+constexpr int kTilesPerWave = kHq / kWaves;              // CTA tiles (quarters) side by side in one wave
+constexpr int kFc1N = 256, kFc2N = 240;                  // weight rows per CTA tile of the two layers
+constexpr int kRedThreads = 3 * kWaves;                  // threads that share one float4 of the split-K reduce
+constexpr int kRedLoads = 14;                            //   each with <= 14 partial loads in flight
+constexpr int kRedGroups = 32 / kRedThreads;             // float4 outputs per warp and pass
+constexpr int kStageCols = 128;                          // TMEM column offset of the second accumulator stage (<= 128 persons)
+constexpr int kBarLine = 16;                             // grid barrier counters sit on separate 128-byte lines
 constexpr int kXBox = 16;                                // rows per activation TMA box (persons are padded to 16)
 constexpr int kXBoxBytes = kXBox * 128;
 constexpr int kXTileBytes = 128 * 128;                   // one 128-row activation tile (16 KB)
@@ -67,7 +77,7 @@ constexpr int kEpiWarps = 16;                           // 4 per TMEM lane quadr
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 16 x 32 fp32 boxes of the in-place epilogue
 constexpr int kBarOffset = kStgOffset + kEpiWarps * 2048;
-constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 2) * 8 + 16 + 1024;
+constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 4) * 8 + 16 + 1024;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -86,7 +96,7 @@ struct FusedArgs {
     const float *b2;
     const float *x;          // fp32 crops [N, D] (residual)
     float *logits;           // [N, D]
-    unsigned long long *arrivals;   // grid barrier: monotonically increasing arrival count (2 * grid per launch)
+    unsigned long long *arrivals;   // grid barriers: 2 * kWaves never-reset arrival counters (grid arrivals per launch each)
     unsigned long long *trace;      // optional [grid, 16] globaltimer stamps (mpn_debug_fused_trace)
 };
 
@@ -102,10 +112,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-// Grid barrier over a counter that is never reset: every launch that gets past the person-count check adds exactly
-// 2 * grid arrivals, so the counter value at kernel entry, rounded down to a multiple of 2 * grid, is this launch's base
-// (no CTA can see more than grid - 1 arrivals of barrier 1 before it has arrived itself).  All CTAs are co-resident
-// (cooperative launch).  One thread per CTA arrives; one round trip to L2 to arrive, one to observe.
+// Grid barriers over counters that are never reset: every launch that gets past the person-count check adds exactly
+// grid arrivals to each of the 2 * kWaves counters (one per meeting point; a CTA may arrive at a later meeting point
+// before a slow CTA has arrived at an earlier one, so they cannot share a counter), so counter 0 at kernel entry, rounded
+// down to a multiple of grid, is this launch's base for all of them (no CTA can see more than grid - 1 arrivals at the
+// first meeting point before it has arrived itself).  All CTAs are co-resident (cooperative launch).  One thread per CTA
+// arrives; one round trip to L2 to arrive, one to observe.
 // (A two-level version -- arrivals on per-group lines, last arrival of a group on a top counter, waiters polling a
 // separate epoch word -- was measured: its three dependent fence + atomic hops cost 3.2 and 4.0 us per barrier against
 // 1.4 and 2.1 us for this one.)
@@ -117,17 +129,21 @@ __device__ __forceinline__ void grid_arrive(unsigned long long *arrivals)
     atomicAdd(arrivals, 1ULL);
 }
 
+__device__ __forceinline__ bool grid_poll(const unsigned long long *arrivals, unsigned long long target)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(arrivals) : "memory");
+    if (v < target) return false;
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    return true;
+}
+
 __device__ __forceinline__ void grid_wait(const unsigned long long *arrivals, unsigned long long target)
 {
     // Poll with RELAXED loads and fence once at the end: an acquire load is compiled to LDG + CCTL.IVALL, and an L1
     // invalidation every few hundred nanoseconds disturbs the memory pipeline of the warps that are still working.
     for (unsigned spin = 0; spin < (1u << 24); ++spin) {
-        unsigned long long v;
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(arrivals) : "memory");
-        if (v >= target) {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            return;
-        }
+        if (grid_poll(arrivals, target)) return;
         __nanosleep(64);
     }
     __trap();
@@ -166,14 +182,15 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     pdl_trigger();
     const int G = gridDim.x, c = blockIdx.x;
     // this launch's barrier base; read before this CTA can possibly have arrived anywhere
-    const unsigned long long bar_base = (ld_acquire_u64(args.arrivals) / (2ull * G)) * (2ull * G);
+    const unsigned long long bar_base = (ld_acquire_u64(args.arrivals) / (unsigned long long)G) * (unsigned long long)G;
+    const unsigned long long bar_target = bar_base + (unsigned long long)G;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kBarOffset);
     uint64_t *empty_bar = full_bar + kMaxStages;
-    uint64_t *tmem_full_bar = empty_bar + kMaxStages;
-    uint64_t *tmem_empty_bar = tmem_full_bar + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + kMaxStages;      // [2]: one per accumulator stage
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -182,8 +199,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_y1)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, kEpiWarps);
+        for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar + i, 1); mbar_init(tmem_empty_bar + i, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 1) {
         tmem_alloc(tmem_slot, kTmemCols);
@@ -194,8 +210,8 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(args, 0);                                   // prologue done
 
-    const bool has_fc1 = c < kHq * args.splits;
-    const int hq = c % kHq, z = c / kHq;
+    const bool has_fc1 = c < kTilesPerWave * args.splits;
+    const int tq = c % kTilesPerWave, z = c / kTilesPerWave;               // quarter inside a wave, K split
     const int kb0 = has_fc1 ? (int)(((long long)z * args.nkb1) / args.splits) : 0;
     const int kb1 = has_fc1 ? (int)(((long long)(z + 1) * args.nkb1) / args.splits) : 0;
 
@@ -208,7 +224,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         early = min(kEarly, kb1 - kb0);
         for (int i = 0; i < early; ++i) {
             mbar_expect_tx(full_bar + i, kFc1N * 128);
-            tma_load_2d(smem + i * kWTileBytes, &tmap_w1, full_bar + i, (kb0 + i) * BLOCK_K, hq * kFc1N, kEvictFirst);
+            tma_load_2d(smem + i * kWTileBytes, &tmap_w1, full_bar + i, (kb0 + i) * BLOCK_K, tq * kFc1N, kEvictFirst);
         }
     }
     pdl_wait();                                                             // crops and person count are complete
@@ -222,6 +238,9 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int n_stages = nm == 1 ? 4 : 3;
     const int x_base = n_stages * kWTileBytes, x_stride = nm * kXTileBytes;
     const uint32_t x_bytes = (uint32_t)nb * kXBoxBytes;
+    // accumulator stages: round r (fc1 waves, then fc2 tiles) accumulates in stage r % n_acc, at TMEM columns
+    // stage * 128 + half * 256; two stages need the persons to fit 128 columns
+    const int n_acc = (kWaves > 1 && nm == 1) ? 2 : 1;
     if (!run) {
         if (threadIdx.x == 0)
             for (int i = 0; i < early; ++i) { mbar_arrive(full_bar + i); mbar_wait(full_bar + i, 0); }   // drain
@@ -230,21 +249,25 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {   // ================= TMA producer =================
             int it = 0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const int st = it % n_stages;
-                uint8_t *xs = smem + x_base + st * x_stride;
-                if (it < early) {       // W box already in flight
-                    mbar_arrive_expect_tx(full_bar + st, x_bytes);
-                } else {
-                    mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
-                    tma_load_2d(smem + st * kWTileBytes, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
+            for (int w = 0; w < kWaves; ++w) {
+                const int hq = w * kTilesPerWave + tq;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int st = it % n_stages;
+                    uint8_t *xs = smem + x_base + st * x_stride;
+                    if (it < early) {       // W box already in flight
+                        mbar_arrive_expect_tx(full_bar + st, x_bytes);
+                    } else {
+                        mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
+                        tma_load_2d(smem + st * kWTileBytes, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
+                    }
+                    for (int b = 0; b < nb; ++b)
+                        tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
                 }
-                for (int b = 0; b < nb; ++b)
-                    tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
             }
             stamp(args, 1);                                                 // all fc1 loads issued
-            // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces.
+            // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces; k
+            // block kb of fc2 needs the y1 columns of wave kb * kWaves / nkb2 only.
             // Measured and not kept (profiles/r01f_summary.md): TMA L2 prefetches of the rest of the W2 tile issued here
             // or after barrier 1, a sliding L2 prefetch window ahead of the ring in both layers, an L2 prefetch of W1
             // from a kernel in the front half of the call, and a per-CTA rotation of the k order.  With W2 L2-resident
@@ -253,45 +276,38 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // the number of W2 boxes on the SM before barrier 2 (profiles/r01g_*.txt).
             const int first2 = it;
             int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
-            bool y1_ready = false;
+            int ready = 0;             // waves of y1 known to be complete
+            auto y1_ready = [&](int i, bool block) -> bool {   // is the y1 k block of iteration i there?
+                const int want = ((i - first2) % args.nkb2) * kWaves / args.nkb2 + 1;
+                while (ready < want) {
+                    const unsigned long long *cnt = args.arrivals + (2 * ready + 1) * kBarLine;
+                    if (block) grid_wait(cnt, bar_target);
+                    else if (!grid_poll(cnt, bar_target)) return false;
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    ++ready;
+                    if (ready == kWaves) stamp(args, 6);                    // producer saw the last y1 barrier
+                }
+                return true;
+            };
+            auto y1_issue = [&](int i) {
+                const int st = i % n_stages;
+                uint8_t *stg = smem + x_base + st * x_stride;
+                for (int b = 0; b < nb; ++b)
+                    tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + st, ((i - first2) % args.nkb2) * BLOCK_K, b * kXBox,
+                                kEvictLast);
+            };
             for (int tile = c; tile < args.tiles2; tile += G) {
                 for (int kb = 0; kb < args.nkb2; ++kb, ++it) {
                     const int st = it % n_stages;
-                    if (!y1_ready && it - first2 >= n_stages) {
-                        grid_wait(args.arrivals, bar_base + 2ull * G);
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        stamp(args, 6);                                     // producer saw barrier 2
-                        y1_ready = true;
-                        for (; flushed < it; ++flushed) {      // only ever the first n_stages k blocks of the first tile
-                            uint8_t *stg = smem + x_base + (flushed % n_stages) * x_stride;
-                            for (int b = 0; b < nb; ++b)
-                                tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
-                                            (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
-                        }
-                    }
+                    // the slot is released by the MMAs of iteration it - n_stages, which need that iteration's y1 boxes
+                    for (; flushed <= it - n_stages; ++flushed) { y1_ready(flushed, true); y1_issue(flushed); }
                     mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc2N * 128);
-                    uint8_t *xs = smem + x_base + st * x_stride;
                     tma_load_2d(smem + st * kWTileBytes, &tmap_w2, full_bar + st, kb * BLOCK_K, tile * kFc2N, kEvictFirst);
-                    if (y1_ready) {
-                        for (int b = 0; b < nb; ++b)
-                            tma_load_2d(xs + b * kXBoxBytes, &tmap_y1, full_bar + st, kb * BLOCK_K, b * kXBox,
-                                        kEvictLast);
-                        flushed = it + 1;
-                    }
+                    for (; flushed <= it && y1_ready(flushed, false); ++flushed) y1_issue(flushed);
                 }
             }
-            if (!y1_ready && it > first2) {
-                grid_wait(args.arrivals, bar_base + 2ull * G);
-                asm volatile("fence.proxy.async;" ::: "memory");
-                stamp(args, 6);
-                for (; flushed < it; ++flushed) {
-                    uint8_t *stg = smem + x_base + (flushed % n_stages) * x_stride;
-                    for (int b = 0; b < nb; ++b)
-                        tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + (flushed % n_stages),
-                                    (flushed - first2) * BLOCK_K, b * kXBox, kEvictLast);
-                }
-            }
+            for (; flushed < it; ++flushed) { y1_ready(flushed, true); y1_issue(flushed); }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -301,32 +317,40 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // (128 N / 256 cycles per instruction) and the TMEM drain all scale with the number of persons.
             const uint32_t idesc = make_idesc_bf16(128, nb * kXBox);
             int it = 0, round = 0;
-            if (has_fc1) {
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int st = it % n_stages;
-                    mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
+            auto acc_stage = [&]() -> uint32_t {   // this round's accumulator columns, drained by the epilogue of round - n_acc
+                const int stage = round % n_acc;
+                if (round >= n_acc) {
+                    mbar_wait(tmem_empty_bar + stage, ((uint32_t)(round / n_acc - 1)) & 1u);
                     tc_fence_after();
-                    const uint32_t w_addr = smem_u32(smem + st * kWTileBytes);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + x_base + st * x_stride));
-#pragma unroll
-                    for (int m = 0; m < kFc1N / 128; ++m) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(empty_bar + st);
                 }
-                umma_commit(tmem_full_bar);
-                ++round;
-                stamp(args, 2);                                             // all fc1 MMAs issued
+                return tmem_base + (uint32_t)(stage * kStageCols);
+            };
+            if (has_fc1) {
+                for (int w = 0; w < kWaves; ++w) {
+                    const uint32_t acc = acc_stage();
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int st = it % n_stages;
+                        mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(smem + st * kWTileBytes);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + x_base + st * x_stride));
+#pragma unroll
+                        for (int m = 0; m < kFc1N / 128; ++m) {
+                            const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16(acc + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                          idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(empty_bar + st);
+                    }
+                    umma_commit(tmem_full_bar + round % n_acc);
+                    ++round;
+                    stamp(args, w == 0 ? 2 : 14);                           // all MMAs of the wave issued
+                }
             }
             for (int tile = c; tile < args.tiles2; tile += G) {
-                if (round > 0) {   // the epilogue has drained the previous accumulators
-                    mbar_wait(tmem_empty_bar, ((uint32_t)(round - 1)) & 1u);
-                    tc_fence_after();
-                }
+                const uint32_t acc = acc_stage();
                 for (int kb = 0; kb < args.nkb2; ++kb, ++it) {
                     const int st = it % n_stages;
                     mbar_wait(full_bar + st, ((uint32_t)(it / n_stages)) & 1u);
@@ -340,12 +364,12 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const uint64_t adesc = make_kmajor_sw128_desc(w_addr + m * kWHalfBytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                            umma_bf16(acc + (uint32_t)(m * kAccCols), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
                                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar + st);
                 }
-                umma_commit(tmem_full_bar);
+                umma_commit(tmem_full_bar + round % n_acc);
                 ++round;
             }
         }
@@ -358,92 +382,96 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // persons.  No transpose: a warp-wide store of r[j] IS the coalesced row segment of person j.
         const int ew = warp - 2, q = warp & 3, cg = ew >> 2;
         const int tid_e = threadIdx.x - 64;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         float *stg = reinterpret_cast<float *>(smem + kStgOffset + ew * 2048);
         const int n_items = 2 * nb;
         int round = 0;
-        if (has_fc1) {   // ---- fc1 partial sums: partial[z][person][hq*256 + m*128 + q*32 + lane]
-            mbar_wait(tmem_full_bar, 0);
-            tc_fence_after();
-            if (tid_e == 0) stamp(args, 3);                                 // fc1 accumulators complete
-            for (int item = cg; item < (kFc1N / 128) * nb; item += 4) {
-                const int m = item >= nb ? 1 : 0, ch = item - m * nb;
-                uint32_t r[16];
-                tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
-                if (tid_e == 0 && item == cg) stamp(args, 11);              // warp 2: first accumulator item in registers
-                float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(ch * 16) * args.hidden + hq * kFc1N +
-                             m * 128 + q * 32 + lane;
+        for (int w = 0; w < kWaves; ++w) {
+            const int col0 = w * (args.hidden / kWaves);                    // first hidden unit of the wave
+            if (has_fc1) {   // ---- fc1 partial sums: partial[z][person][hq*256 + m*128 + q*32 + lane]
+                const int stage = round % n_acc, hq = w * kTilesPerWave + tq;
+                const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * kStageCols);
+                mbar_wait(tmem_full_bar + stage, ((uint32_t)(round / n_acc)) & 1u);
+                tc_fence_after();
+                if (tid_e == 0) stamp(args, w == 0 ? 3 : 13);               // the wave's accumulators are complete
+                for (int item = cg; item < (kFc1N / 128) * nb; item += 4) {
+                    const int m = item >= nb ? 1 : 0, ch = item - m * nb;
+                    uint32_t r[16];
+                    tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
+                    float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(ch * 16) * args.hidden + hq * kFc1N +
+                                 m * 128 + q * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (ch * 16 + j < N) __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
+                    for (int j = 0; j < 16; ++j)
+                        if (ch * 16 + j < N) __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar + stage);
+                ++round;
             }
-            if (tid_e == 0) stamp(args, 12);                                // warp 2: its partial sums issued
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
-            ++round;
-        }
-        epi_bar_sync();
-        if (tid_e == 0) {
-            stamp(args, 4);                                                 // partial sums stored
-            grid_arrive(args.arrivals);
-            grid_wait(args.arrivals, bar_base + (unsigned long long)G);
-            stamp(args, 5);                                                 // barrier 1 passed
-        }
-        epi_bar_sync();
-        {   // ---- y1 = relu(sum_z partial + b1) in bf16: this CTA's slice of the N x hidden outputs, float4 at a time.
-            // Three threads per output vector (lanes 30 and 31 of a warp idle), each with its <= 14 partial loads in
-            // flight at once (one L2 round trip), then a fixed-order combine (s0 + s1) + s2: deterministic, no atomics
-            // on data, and the same association whatever the person count.  160 vectors per pass: one pass up to 92
-            // persons on 148 SMs (four threads per vector needed a second, nearly empty pass above 74).
-            const int vec_per_row = args.hidden >> 2;
-            const int total = N * vec_per_row;
-            const int per = (total + G - 1) / G;
-            const int v_end = min(total, (c + 1) * per);
-            const int s_third = (args.splits + 2) / 3;                     // <= 14 (splits <= 40)
-            const int grp = lane / 3, part = lane - 3 * grp;
-            const int s_lo = part * s_third, s_hi = min(args.splits, s_lo + s_third);
-            for (int v0 = c * per; v0 < v_end; v0 += kEpiWarps * 10) {
-                const int v = v0 + ew * 10 + grp;
-                const bool live = lane < 30 && v < v_end;
-                const int row = live ? v / vec_per_row : 0, c4 = live ? v - row * vec_per_row : 0;
-                const float *src = args.partial + (size_t)s_lo * args.split_stride + (size_t)row * args.hidden + c4 * 4;
-                float4 pv[14];
+            epi_bar_sync();
+            if (tid_e == 0) {
+                stamp(args, w == 0 ? 4 : 11);                               // partial sums stored
+                grid_arrive(args.arrivals + (2 * w) * kBarLine);
+                grid_wait(args.arrivals + (2 * w) * kBarLine, bar_target);
+                stamp(args, w == 0 ? 5 : 12);                               // every CTA's partial sums of the wave are there
+            }
+            epi_bar_sync();
+            {   // ---- y1 = relu(sum_z partial + b1) in bf16: this CTA's slice of the wave's N x (hidden / kWaves) outputs,
+                // float4 at a time.  kRedThreads threads per output vector (the last lanes of a warp idle), each with its
+                // <= 14 partial loads in flight at once (one L2 round trip), then a fixed-order combine ((s0 + s1) + s2)
+                // ...: deterministic, no atomics on data, and the same association whatever the person count.
+                const int vec_per_row = (args.hidden / kWaves) >> 2;
+                const int total = N * vec_per_row;
+                const int per = (total + G - 1) / G;
+                const int v_end = min(total, (c + 1) * per);
+                const int s_part = (args.splits + kRedThreads - 1) / kRedThreads;   // <= kRedLoads
+                const int grp = lane / kRedThreads, part = lane - kRedThreads * grp;
+                const int s_lo = part * s_part, s_hi = min(args.splits, s_lo + s_part);
+                for (int v0 = c * per; v0 < v_end; v0 += kEpiWarps * kRedGroups) {
+                    const int v = v0 + ew * kRedGroups + grp;
+                    const bool live = lane < kRedGroups * kRedThreads && v < v_end;
+                    const int row = live ? v / vec_per_row : 0, c4 = live ? v - row * vec_per_row : 0;
+                    const float *src = args.partial + (size_t)s_lo * args.split_stride + (size_t)row * args.hidden + col0 + c4 * 4;
+                    float4 pv[kRedLoads];
 #pragma unroll
-                for (int i = 0; i < 14; ++i)
-                    pv[i] = (live && s_lo + i < s_hi) ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t)i * args.split_stride))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 acc = pv[0];
+                    for (int i = 0; i < kRedLoads; ++i)
+                        pv[i] = (live && s_lo + i < s_hi) ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t)i * args.split_stride))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 acc = pv[0];
 #pragma unroll
-                for (int i = 1; i < 14; ++i) {
-                    if (s_lo + i < s_hi) {
-                        acc.x = __fadd_rn(acc.x, pv[i].x); acc.y = __fadd_rn(acc.y, pv[i].y);
-                        acc.z = __fadd_rn(acc.z, pv[i].z); acc.w = __fadd_rn(acc.w, pv[i].w);
+                    for (int i = 1; i < kRedLoads; ++i) {
+                        if (s_lo + i < s_hi) {
+                            acc.x = __fadd_rn(acc.x, pv[i].x); acc.y = __fadd_rn(acc.y, pv[i].y);
+                            acc.z = __fadd_rn(acc.z, pv[i].z); acc.w = __fadd_rn(acc.w, pv[i].w);
+                        }
+                    }
+                    float4 tot = acc;                                       // + the sums of lanes g*kRedThreads + 1, + 2, ...
+#pragma unroll
+                    for (int k = 1; k < kRedThreads; ++k) {
+                        tot.x = __fadd_rn(tot.x, __shfl_down_sync(0xffffffffu, acc.x, k));
+                        tot.y = __fadd_rn(tot.y, __shfl_down_sync(0xffffffffu, acc.y, k));
+                        tot.z = __fadd_rn(tot.z, __shfl_down_sync(0xffffffffu, acc.z, k));
+                        tot.w = __fadd_rn(tot.w, __shfl_down_sync(0xffffffffu, acc.w, k));
+                    }
+                    if (live && part == 0) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(args.b1 + col0 + c4 * 4));
+                        tot.x = fmaxf(__fadd_rn(tot.x, bb.x), 0.0f);
+                        tot.y = fmaxf(__fadd_rn(tot.y, bb.y), 0.0f);
+                        tot.z = fmaxf(__fadd_rn(tot.z, bb.z), 0.0f);
+                        tot.w = fmaxf(__fadd_rn(tot.w, bb.w), 0.0f);
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(tot.x, tot.y), hi = __floats2bfloat162_rn(tot.z, tot.w);
+                        uint2 o;
+                        o.x = *reinterpret_cast<const unsigned *>(&lo);
+                        o.y = *reinterpret_cast<const unsigned *>(&hi);
+                        __stcg(reinterpret_cast<uint2 *>(args.y1 + (size_t)row * args.hidden + col0 + c4 * 4), o);
                     }
                 }
-                float4 s1, s2;                                              // the sums of lanes 3g + 1 and 3g + 2
-                s1.x = __shfl_down_sync(0xffffffffu, acc.x, 1); s1.y = __shfl_down_sync(0xffffffffu, acc.y, 1);
-                s1.z = __shfl_down_sync(0xffffffffu, acc.z, 1); s1.w = __shfl_down_sync(0xffffffffu, acc.w, 1);
-                s2.x = __shfl_down_sync(0xffffffffu, acc.x, 2); s2.y = __shfl_down_sync(0xffffffffu, acc.y, 2);
-                s2.z = __shfl_down_sync(0xffffffffu, acc.z, 2); s2.w = __shfl_down_sync(0xffffffffu, acc.w, 2);
-                if (live && part == 0) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(args.b1 + c4 * 4));
-                    acc.x = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.x, s1.x), s2.x), bb.x), 0.0f);
-                    acc.y = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.y, s1.y), s2.y), bb.y), 0.0f);
-                    acc.z = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.z, s1.z), s2.z), bb.z), 0.0f);
-                    acc.w = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(acc.w, s1.w), s2.w), bb.w), 0.0f);
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-                    uint2 o;
-                    o.x = *reinterpret_cast<const unsigned *>(&lo);
-                    o.y = *reinterpret_cast<const unsigned *>(&hi);
-                    __stcg(reinterpret_cast<uint2 *>(args.y1 + (size_t)row * args.hidden + c4 * 4), o);
-                }
             }
-        }
-        epi_bar_sync();
-        if (tid_e == 0) {
-            stamp(args, 8);                                                 // y1 slice stored
-            grid_arrive(args.arrivals);
+            epi_bar_sync();
+            if (tid_e == 0) {
+                stamp(args, w == 0 ? 8 : 15);                               // y1 slice of the wave stored
+                grid_arrive(args.arrivals + (2 * w + 1) * kBarLine);
+            }
         }
         // ---- fc2 epilogue: logits = x + relu(acc + b2)   (detector/prn.py:22,24)
         // Lane = output column n0 + m*128 + q*32 + lane (its bias sits in a register), columns of the item = 16 persons.
@@ -457,7 +485,9 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int tc = m * 128 + q * 32 + lane;
                 bias[m] = (tc < kFc2N && n0 + tc < args.D) ? __ldg(args.b2 + n0 + tc) : 0.0f;
             }
-            mbar_wait(tmem_full_bar, ((uint32_t)round) & 1u);
+            const int stage = round % n_acc;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * kStageCols);
+            mbar_wait(tmem_full_bar + stage, ((uint32_t)(round / n_acc)) & 1u);
             tc_fence_after();
             if (tid_e == 0) stamp(args, 9);                                 // fc2 accumulators complete
             for (int item = cg; item < n_items; item += 4) {
@@ -498,9 +528,8 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty_bar)) : "memory");
+            if (lane == 0) mbar_arrive(tmem_empty_bar + stage);
             ++round;
-            if (tid_e == 0) stamp(args, 15);                                // warp 2 finished the fc2 epilogue
         }
         if (kInPlace && lane == 0) tma_store_wait_all();                    // this thread's reduce-adds have completed
         if (tid_e == 0) stamp(args, 10);                                    // logits stored
@@ -529,7 +558,7 @@ int prn_fused_prepare(mpn_handle *h)
     int dev = h->cfg.device, sms = 0, coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop || sms < kHq) return MPN_OK;
+    if (!coop || sms < kTilesPerWave) return MPN_OK;
     if (cudaFuncSetAttribute(prn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(prn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel<true>, kThreads, kSmemBytes) != cudaSuccess ||
@@ -541,16 +570,16 @@ int prn_fused_prepare(mpn_handle *h)
     FusedState *st = new FusedState;
     memset(st, 0, sizeof(*st));
     st->grid = sms;
-    st->splits = sms / kHq;
+    st->splits = sms / kTilesPerWave;
     const int nkb1 = (D + BLOCK_K - 1) / BLOCK_K;
     if (st->splits > nkb1) st->splits = nkb1;
-    if (st->splits > 40) st->splits = 40;            // the reduce keeps <= 20 partial loads per thread in flight
+    if (st->splits > kRedThreads * kRedLoads) st->splits = kRedThreads * kRedLoads;   // partial loads one reduce thread keeps in flight
     st->rows_cap = h->prn_ws.n_max < kPrnFusedMaxRows ? h->prn_ws.n_max : kPrnFusedMaxRows;
     st->split_stride = (size_t)st->rows_cap * Hd;
     const uint64_t rows = (uint64_t)h->prn_ws.n_max;
     bool ok = cudaMalloc(&st->partial, (size_t)st->splits * st->split_stride * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&st->bar, sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMemset(st->bar, 0, sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc(&st->bar, 2 * kWaves * kBarLine * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(st->bar, 0, 2 * kWaves * kBarLine * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && encode_2d(&st->maps.x, h->crops_bf16, rows, (uint64_t)D, kXBox) &&
          encode_2d(&st->maps.w1, h->W1t, (uint64_t)Hd, (uint64_t)D, kFc1N) &&
          encode_2d(&st->maps.y1, h->prn_ws.y1_bf16, rows, (uint64_t)Hd, kXBox) &&

@@ -13,9 +13,11 @@ flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 for _ in range(3):
     det.prn(x, "bf16", inplace=True)
 det.fused_trace(True)
-names = {7: "pdl wait passed", 0: "prologue", 1: "fc1 loads issued", 2: "fc1 mma issued", 3: "fc1 acc complete", 4: "partials stored",
-         11: "w2 fc1 item 0 in regs", 12: "w2 fc1 partials issued",
-         15: "w2 fc2 epilogue done", 5: "barrier1 passed", 8: "y1 stored", 6: "producer past barrier2", 9: "fc2 acc complete", 10: "logits stored"}
+# wave B slots stay empty in the one-wave build of the kernel (MPN_FC1_WAVES, csrc/prn_fused.cu)
+names = {7: "pdl wait passed", 0: "prologue", 1: "fc1 loads issued", 2: "fc1 A mma issued", 14: "fc1 B mma issued",
+         3: "fc1 A acc complete", 4: "partials A stored", 5: "barrier A1 passed", 8: "y1 A stored",
+         13: "fc1 B acc complete", 11: "partials B stored", 12: "barrier B1 passed", 15: "y1 B stored",
+         6: "producer saw last y1", 9: "fc2 acc complete", 10: "logits stored"}
 for rep in range(3):
     # many launches back to back so that the SM clock is at its loaded value; the trace holds the last launch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,7 +29,7 @@ for rep in range(3):
     t = det.fused_trace(True).astype(np.int64)
     t0 = t[:, 0].min()
     print(f"--- rep {rep}: N={n}, {e0.elapsed_time(e1) * 1e3 / 200:.1f} us per call (f32->bf16 convert + fused kernel)")
-    for slot in (0, 7, 1, 2, 3, 11, 12, 4, 5, 8, 6, 9, 15, 10):
+    for slot in (0, 7, 2, 3, 4, 5, 8, 1, 14, 13, 11, 12, 15, 6, 9, 10):
         col = t[:, slot]
         col = col[col > 0] - t0
         if col.size:
