@@ -204,7 +204,7 @@ int do_detect(mpn_handle *h, const mpn_inputs *in, const mpn_params *p, float *b
 }
 
 int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const int *n_dev, int n_host, int n_max,
-           int mode, float *logits, cudaStream_t s, bool first)
+           int mode, float *logits, cudaStream_t s, bool first, const FusedCropCall *fc = nullptr)
 {
     if (!h->have_weights) return fail(h, MPN_ERR_NO_WEIGHTS, "mpn_set_prn_weights has not been called");
     PrnWeights w;
@@ -219,7 +219,7 @@ int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const
     // known on the device, so when the call's capacity exceeds 256 both are launched and each exits at once outside
     // its regime.
     if (h->fused) {
-        int rc = launched(h, launch_prn_fused(h, x_f32, n_dev, n_host, logits, s), first, "prn fused");
+        int rc = launched(h, launch_prn_fused(h, x_f32, n_dev, n_host, logits, s, fc), first, "prn fused");
         if (rc || n_max <= kPrnFusedMaxRows) return rc;
         first = false;
     }
@@ -376,6 +376,10 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_cand, cudaEventDisableTiming);
     h->cfg_use_graphs = getenv("MPN_NO_GRAPH") == nullptr;
     h->use_pdl = getenv("MPN_NO_PDL") == nullptr;
+    {   // crop_and_resize inside the single-kernel PRN (prn_fused.cu: CropFuse); MPN_FUSE_CROP=0/1 overrides the default
+        const char *fc = getenv("MPN_FUSE_CROP");
+        h->fuse_crop = fc ? fc[0] == '1' : false;
+    }
     if (e != cudaSuccess) {
         fail(nullptr, MPN_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
         mpn_destroy(h);
@@ -735,7 +739,12 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     pl.num_boxes = out->num_boxes; pl.det_boxes = out->boxes; pl.B = in->batch; pl.max_det = p->max_detections;
     pl.person_box = h->person_box; pl.person_img = h->person_img; pl.person_offsets = h->person_offsets;
     pl.person_offsets_out = out->person_offsets;
-    if (!(skip & 8u))
+    // Calls that fit the single-kernel PRN (capacity <= 256 persons, padded map, in place) can leave the crop to it: its
+    // epilogue warps sample while the weights stream (prn_fused.cu: CropFuse), and the crop kernel is not launched.
+    // Skip bit 64 (development aid): that kernel samples and stops, so that the crops can be fetched.
+    const bool fuse = h->fuse_crop && padded && bf16 && n_max <= kPrnFusedMaxRows && prn_fused_can_crop(h, in->batch) &&
+                      !(skip & (8u | 16u));
+    if (!(skip & 8u) && !fuse)
         rc = launched(h, padded ? launch_crop_padded(h->nh_ws, hh, ww, pl, n_max, h->cfg.crop_height, h->cfg.crop_width,
                                                      h->crops_f32, bf16 ? h->crops_bf16 : nullptr, s)
                                 : launch_crop(kh, h->minmax_ws, hh, ww, pl, n_max, h->cfg.crop_height, h->cfg.crop_width,
@@ -748,7 +757,12 @@ static int enqueue_path(mpn_handle *h, const mpn_inputs *in, const mpn_params *p
     float *prn_out = (bf16 && (h->big || (h->fused && n_max <= kPrnFusedMaxRows))) ? h->crops_f32 : h->logits;
     h->last_run.batch = in->batch; h->last_run.hh = hh; h->last_run.ww = ww; h->last_run.n_max = n_max;
     h->last_run.padded = padded; h->last_run.prn_out = prn_out; h->last_run.valid = true;
-    if (!(skip & 16u)) rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, prn_out, s, false);
+    FusedCropCall fc;
+    if (fuse) {
+        fc.nh = h->nh_ws; fc.hh = hh; fc.ww = ww; fc.pl = pl; fc.only = (skip & 64u) ? 1 : 0;
+    }
+    if (!(skip & 16u))
+        rc = do_prn(h, h->crops_f32, h->crops_bf16, n_dev, 0, n_max, p->prn_mode, prn_out, s, false, fuse ? &fc : nullptr);
     if (rc) return rc;
     // 5. softmax / argmax                                    (create_pb.py:115-142)
     if (skip & 32u) return MPN_OK;

@@ -48,6 +48,7 @@ struct mpn_handle {
     const float *const *enc_indirect;   // set around the mpn_run of a host call (see DetectArgs::enc_ind)
     bool use_pdl;           // programmatic dependent launch between consecutive kernels of a branch
     unsigned debug_skip;    // mpn_debug_skip: bit i set = stage i is not launched (timing experiments only)
+    bool fuse_crop;         // crop_and_resize inside the single-kernel PRN where the call allows it (MPN_FUSE_CROP)
     // detect workspace
     unsigned long long *cand_keys;
     int *cand_count;
@@ -103,5 +104,15 @@ int launch_prn_big(mpn_handle *h, const float *x_f32, const int *n_dev, int n_ho
 int prn_fused_prepare(mpn_handle *h);  // prn_fused.cu: persistent single-kernel PRN for <= kPrnFusedMaxRows persons
 void prn_fused_release(mpn_handle *h);
 int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int capacity, int *grid_out);
-int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s);
+// fc != NULL: crop_and_resize of the padded normalised map runs inside the kernel (prn_fused.cu: CropFuse); x_f32 must be
+// logits (in place), the person list is derived from the detection outputs and written by the kernel
+struct FusedCropCall {
+    const float *nh;
+    int hh, ww;
+    PersonList pl;
+    int only;               // development aid: sample the crops (bf16 and fp32) and stop
+};
+bool prn_fused_can_crop(const mpn_handle *h, int batch);
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s,
+                     const FusedCropCall *fc = nullptr);
 }

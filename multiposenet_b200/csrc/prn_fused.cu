@@ -37,6 +37,7 @@
 
 #include "common.cuh"
 #include "handle.cuh"
+#include "mpn_math.cuh"
 #include "tcgen05_utils.cuh"
 
 namespace mpn {
@@ -77,11 +78,35 @@ constexpr int kEpiWarps = 16;                           // 4 per TMEM lane quadr
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kStgOffset = kRingBytes;                   // 16 x 2 KB: per-warp 16 x 32 fp32 boxes of the in-place epilogue
 constexpr int kBarOffset = kStgOffset + kEpiWarps * 2048;
-constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+constexpr int kOffOffset = kBarOffset + (2 * kMaxStages + 4) * 8 + 16;   // fused crop: person offsets of <= 256 images, u16
+constexpr int kSmemBytes = kOffOffset + 528 + 1024;
 constexpr uint32_t kTmemCols = 512;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
+// crop_and_resize (create_pb.py:106-109) inside this kernel, for calls of mpn_run that fit it (padded normalised map,
+// capacity <= 256 persons, in place): the crop kernel, its launch and its 16 MB round trip through L2 leave the call's
+// critical chain.  The epilogue warps are idle while a layer streams, and that is when they sample --
+//   during fc1: the bf16 operand.  The four CTAs of a K split (one per hidden quarter) consume the same 928 crop columns of
+//     every person; each of them samples a quarter of the persons (in chunks of kCropChunk k blocks, staged in shared memory,
+//     written to crops_bf16 as 16-byte vectors) and publishes the chunk on a counter of its split; the TMA producer
+//     fetches the activation boxes of a k block when the four parts of its chunk are there.  The weight boxes do not wait.
+//   during fc2: the fp32 residual.  The CTA samples the 240 columns of its own output tile for every person and stores
+//     them where the TMA reduce-add of its epilogue then adds relu(acc + b2): nobody else touches those columns.
+// The arithmetic is crop_padded_kernel's (heatmap.cu), operation for operation: same bits.
+struct CropFuse {
+    const float *nh;          // padded normalised map [B, hh, ww, 20]; NULL: the crops are in memory already
+    int hh, ww;
+    PersonList pl;            // derived mode: num_boxes, det_boxes, B (<= 256), max_det + where the flat list goes
+    __nv_bfloat16 *x_bf16;    // [rows, D]: written here, fetched by TMA (tmap_x)
+    unsigned long long *xready;   // [splits, 4] never-reset counters: 4 arrivals per launch and chunk in use
+    int only;                 // development aid: sample (both forms) and stop
+};
+constexpr int kCropH = 56, kCropW = 36, kCropCh = 17, kCropPad = 20, kCropGroups = 5;
+constexpr int kCropChunk = 5;                            // k blocks per published chunk of the bf16 operand (<= 4 chunks)
+constexpr int kStgRows = kEpiWarps * 2048 / 128;         // 128-byte rows of the staging area (256)
+
 struct FusedArgs {
+    CropFuse crop;
     const int *n_dev;
     int n_host;
     int D, hidden;
@@ -168,10 +193,130 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
+// ---- crop_and_resize sampling (fused crop; crop_padded_kernel's arithmetic) --------------------------------------------------
+struct CropGeo {
+    float ay, hs, ax, ws;             // in_y = ay + cy * hs, in_x = ax + cx * ws
+    const float4 *img;                // the person's image in the padded normalised map
+};
+
+// Person `row` of the flat list (create_pb.py:96-103) is box k of image b, where s_off (exclusive scan of num_boxes, B + 1
+// entries) brackets row.
+__device__ __forceinline__ CropGeo crop_geo(const CropFuse &cf, const unsigned short *s_off, int row)
+{
+    int lo = 0, hi = cf.pl.B;                          // s_off[lo] <= row < s_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)s_off[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int k = row - (int)s_off[lo];
+    const float4 box = __ldcg(reinterpret_cast<const float4 *>(cf.pl.det_boxes) + (lo * cf.pl.max_det + k));
+    const float hm1 = (float)(cf.hh - 1), wm1 = (float)(cf.ww - 1);
+    CropGeo g;
+    g.hs = fdiv(fmul(fsub(box.z, box.x), hm1), (float)(kCropH - 1));
+    g.ay = fmul(box.x, hm1);
+    g.ws = fdiv(fmul(fsub(box.w, box.y), wm1), (float)(kCropW - 1));
+    g.ax = fmul(box.y, wm1);
+    g.img = reinterpret_cast<const float4 *>(cf.nh + (size_t)lo * cf.hh * cf.ww * kCropPad);
+    return g;
+}
+
+struct CropTaps {
+    float4 tl, tr, bl, br;
+    float lx, ly;
+    bool inside;
+};
+
+// the four taps of channels 4 grp .. 4 grp + 3 at crop pixel p = cy * 36 + cx (loads only)
+__device__ __forceinline__ CropTaps crop_taps(const CropGeo &g, int hh, int ww, int p, int grp)
+{
+    const int cy = p / kCropW, cx = p - cy * kCropW;
+    const float in_y = fadd(g.ay, fmul((float)cy, g.hs)), in_x = fadd(g.ax, fmul((float)cx, g.ws));
+    CropTaps t;
+    t.inside = !(in_y < 0.0f || in_y > (float)(hh - 1)) && !(in_x < 0.0f || in_x > (float)(ww - 1));
+    const int top = (int)floorf(in_y), bot = (int)ceilf(in_y), left = (int)floorf(in_x), right = (int)ceilf(in_x);
+    t.ly = fsub(in_y, (float)top);
+    t.lx = fsub(in_x, (float)left);
+    const unsigned o_tl = t.inside ? (unsigned)((top * ww + left) * kCropGroups + grp) : 0u;
+    const unsigned o_tr = t.inside ? (unsigned)((top * ww + right) * kCropGroups + grp) : 0u;
+    const unsigned o_bl = t.inside ? (unsigned)((bot * ww + left) * kCropGroups + grp) : 0u;
+    const unsigned o_br = t.inside ? (unsigned)((bot * ww + right) * kCropGroups + grp) : 0u;
+    t.tl = __ldg(g.img + o_tl); t.tr = __ldg(g.img + o_tr); t.bl = __ldg(g.img + o_bl); t.br = __ldg(g.img + o_br);
+    return t;
+}
+
+__device__ __forceinline__ float crop_lerp(float tl, float tr, float bl, float br, float lx, float ly, bool inside)
+{
+    const float tpv = fadd(tl, fmul(fsub(tr, tl), lx));
+    const float btv = fadd(bl, fmul(fsub(br, bl), lx));
+    return inside ? fadd(tpv, fmul(fsub(btv, tpv), ly)) : 0.0f;
+}
+
+__device__ __forceinline__ void crop_values(const CropTaps &t, float o[4])
+{
+    o[0] = crop_lerp(t.tl.x, t.tr.x, t.bl.x, t.br.x, t.lx, t.ly, t.inside);
+    o[1] = crop_lerp(t.tl.y, t.tr.y, t.bl.y, t.br.y, t.lx, t.ly, t.inside);
+    o[2] = crop_lerp(t.tl.z, t.tr.z, t.bl.z, t.br.z, t.lx, t.ly, t.inside);
+    o[3] = crop_lerp(t.tl.w, t.tr.w, t.bl.w, t.br.w, t.lx, t.ly, t.inside);
+}
+
+// Samples columns [kA, kB) of person rows first, first + step, ... (n_rows of them, rows >= N skipped) into a staging image
+// of `rowlen` T per row: threads-per-row x rows-at-once is chosen from the row count; two items (8 tap loads) in flight
+// per thread.  Called by all epilogue warps.
+template <typename T>
+__device__ __forceinline__ void crop_sample_rows(const CropFuse &cf, const unsigned short *s_off, int N, int first, int step,
+                                                 int n_rows, int kA, int kB, T *stg, int rowlen, int tid_e)
+{
+    const int tp = (kEpiWarps * 32) / n_rows;          // threads per row (n_rows <= 512)
+    const int pi = tid_e / tp, sub = tid_e - pi * tp;
+    const int row = first + pi * step;
+    if (pi >= n_rows || row >= N) return;
+    const CropGeo g = crop_geo(cf, s_off, row);
+    const int p_lo = kA / kCropCh, p_hi = (kB - 1) / kCropCh;
+    const int n_items = (p_hi - p_lo + 1) * kCropGroups;
+    T *dst = stg + (size_t)pi * rowlen - kA;
+    auto put = [&](int p, int grp, const float o[4]) {
+        const int k0 = p * kCropCh + 4 * grp;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = k0 + t;
+            if ((t == 0 || grp < kCropGroups - 1) && k >= kA && k < kB) {     // group 4 holds channel 16 only
+                if (sizeof(T) == 2) reinterpret_cast<__nv_bfloat16 *>(dst)[k] = __float2bfloat16_rn(o[t]);
+                else reinterpret_cast<float *>(dst)[k] = o[t];
+            }
+        }
+    };
+    for (int j = sub; j < n_items; j += 2 * tp) {
+        const int j2 = j + tp;
+        const int pa = p_lo + j / kCropGroups, ga = j - (j / kCropGroups) * kCropGroups;
+        const bool two = j2 < n_items;
+        const int pb = two ? p_lo + j2 / kCropGroups : pa, gb = two ? j2 - (j2 / kCropGroups) * kCropGroups : ga;
+        const CropTaps ta = crop_taps(g, cf.hh, cf.ww, pa, ga);
+        const CropTaps tb = crop_taps(g, cf.hh, cf.ww, pb, gb);
+        float o[4];
+        crop_values(ta, o);
+        put(pa, ga, o);
+        if (two) {
+            crop_values(tb, o);
+            put(pb, gb, o);
+        }
+    }
+}
+
+// number of persons of the call = sum of num_boxes (every warp for itself: one L2 round trip)
+__device__ __forceinline__ int crop_count_persons(const PersonList &pl, int lane)
+{
+    int n = 0;
+    for (int b0 = 0; b0 < pl.B; b0 += 32) n += (b0 + lane < pl.B) ? __ldcg(pl.num_boxes + b0 + lane) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    return n;
+}
+
 // kInPlace: logits == x (how mpn_run calls it).  The fc2 epilogue then never loads the residual: bias and ReLU are applied
 // in registers, the 16-person x 32-column item goes to the warp's staging box (dense rows, no swizzle) and a TMA reduce-add performs
 // x += y2 in L2 -- the same single fp32 rounding, no residual registers, 4 B / element less L2 -> SM traffic.
-template <bool kInPlace>
+// kCrop: the instantiation that can sample the crops itself (CropFuse); the others carry none of that code.
+template <bool kInPlace, bool kCrop>
 __global__ void __launch_bounds__(kThreads, 1)
 prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,
@@ -227,9 +372,58 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tma_load_2d(smem + i * kWTileBytes, &tmap_w1, full_bar + i, (kb0 + i) * BLOCK_K, tq * kFc1N, kEvictFirst);
         }
     }
-    pdl_wait();                                                             // crops and person count are complete
+    // fused crop: this launch's base of the chunk counters of split z (read before any of the four CTAs can have arrived)
+    const bool crop = kCrop && kInPlace && kWaves == 1 && args.crop.nh != nullptr;
+    unsigned long long x_target[4] = {0, 0, 0, 0};
+    if (crop && threadIdx.x == 0 && has_fc1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x_target[i] = (ld_acquire_u64(args.crop.xready + z * 4 + i) / 4ull) * 4ull + 4ull;
+    }
+    pdl_wait();                                        // crops and person count (fused crop: map and detections) are complete
     if (threadIdx.x == 0) stamp(args, 7);
-    const int N = args.n_dev ? *args.n_dev : args.n_host;
+    const int N = crop ? crop_count_persons(args.crop.pl, lane) : (args.n_dev ? *args.n_dev : args.n_host);
+    unsigned short *s_off = reinterpret_cast<unsigned short *>(smem + kOffOffset);
+    if (crop && warp >= 2) {
+        // exclusive scan of num_boxes -> shared memory (every CTA); the last CTA also writes the flat person list and the
+        // offsets for whoever wants them afterwards (decode kernel, person_offsets output, mpn_debug_fetch)
+        const PersonList &pl = args.crop.pl;
+        const int te = threadIdx.x - 64;
+        if (warp == 2) {
+            int running = 0;
+            for (int b0 = 0; b0 < pl.B; b0 += 32) {
+                const int b = b0 + lane;
+                const int nbx = (b < pl.B) ? __ldcg(pl.num_boxes + b) : 0;
+                int incl = nbx;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (b < pl.B) s_off[b] = (unsigned short)(running + incl - nbx);
+                running += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_off[pl.B] = (unsigned short)running;
+        }
+        epi_bar_sync();
+        if (c == G - 1) {
+            for (int b = te; b <= pl.B; b += kEpiWarps * 32) {
+                pl.person_offsets[b] = (int)s_off[b];
+                if (pl.person_offsets_out) pl.person_offsets_out[b] = (int)s_off[b];
+            }
+            if (pl.person_box)
+                for (int idx = te; idx < pl.B * pl.max_det; idx += kEpiWarps * 32) {
+                    const int b = idx / pl.max_det, k = idx - b * pl.max_det;
+                    if (k < (int)s_off[b + 1] - (int)s_off[b]) {
+                        const int row = (int)s_off[b] + k;
+                        reinterpret_cast<float4 *>(pl.person_box)[row] = __ldcg(reinterpret_cast<const float4 *>(pl.det_boxes) + idx);
+                        pl.person_img[row] = b;
+                    }
+                }
+        }
+    }
+    // bf16 operand of the fused crop: chunks of `cb` k blocks, the same for the four CTAs of a split
+    const int nkz = kb1 - kb0;
+    const int cb = crop ? max(1, min(kCropChunk, kStgRows / max(1, (N + 3) >> 2))) : 1 << 20;
     const bool run = N > 0 && N <= kPrnFusedMaxRows;   // uniform over the grid; the general kernels take N > 256
     const int nm = (N + 127) >> 7;                   // 128-row M tiles
     const int nb = (N + kXBox - 1) / kXBox;          // 16-row activation boxes
@@ -241,7 +435,8 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // accumulator stages: round r (fc1 waves, then fc2 tiles) accumulates in stage r % n_acc, at TMEM columns
     // stage * 128 + half * 256; two stages need the persons to fit 128 columns
     const int n_acc = (kWaves > 1 && nm == 1) ? 2 : 1;
-    if (!run) {
+    const bool only = crop && args.crop.only != 0;     // development aid: sample and stop
+    if (!run || (only && warp < 2)) {
         if (threadIdx.x == 0)
             for (int i = 0; i < early; ++i) { mbar_arrive(full_bar + i); mbar_wait(full_bar + i, 0); }   // drain
     } else
@@ -249,11 +444,38 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {   // ================= TMA producer =================
             int it = 0;
+            // fused crop: the activation boxes of a k block are requested when the four CTAs of the split have published
+            // its chunk; the weight boxes do not wait for them (xfl = fc1 iterations whose activation boxes are issued,
+            // kept with its chunk / position incrementally; xrdy = chunks known to be complete)
+            int xfl = 0, xch = 0, xin = 0, xrdy = 0;
+            auto x_ready = [&](bool block) -> bool {
+                while (xrdy <= xch) {
+                    const unsigned long long *cnt = args.crop.xready + z * 4 + xrdy;
+                    const unsigned long long target = xrdy == 0 ? x_target[0] : xrdy == 1 ? x_target[1] : xrdy == 2 ? x_target[2] : x_target[3];
+                    if (block) grid_wait(cnt, target);
+                    else if (!grid_poll(cnt, target)) return false;
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    ++xrdy;
+                }
+                return true;
+            };
+            auto x_issue = [&]() {
+                const int st = xfl % n_stages;
+                uint8_t *xs = smem + x_base + st * x_stride;
+                for (int b = 0; b < nb; ++b)
+                    tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, (kb0 + xfl) * BLOCK_K, b * kXBox, kEvictLast);
+                ++xfl;
+                if (++xin == cb) { xin = 0; ++xch; }
+            };
             for (int w = 0; w < kWaves; ++w) {
                 const int hq = w * kTilesPerWave + tq;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int st = it % n_stages;
                     uint8_t *xs = smem + x_base + st * x_stride;
+                    if (crop && xfl <= it - n_stages) {   // the slot's previous user needs its activation boxes first
+                        while (xfl <= it - n_stages) { x_ready(true); x_issue(); }
+                        while (xfl < it && x_ready(false)) x_issue();
+                    }
                     if (it < early) {       // W box already in flight
                         mbar_arrive_expect_tx(full_bar + st, x_bytes);
                     } else {
@@ -261,10 +483,15 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc1N * 128);
                         tma_load_2d(smem + st * kWTileBytes, &tmap_w1, full_bar + st, kb * BLOCK_K, hq * kFc1N, kEvictFirst);
                     }
-                    for (int b = 0; b < nb; ++b)
-                        tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
+                    if (!crop) {
+                        for (int b = 0; b < nb; ++b)
+                            tma_load_2d(xs + b * kXBoxBytes, &tmap_x, full_bar + st, kb * BLOCK_K, b * kXBox, kEvictLast);
+                    } else {
+                        while (xfl <= it && x_ready(false)) x_issue();
+                    }
                 }
             }
+            if (crop) while (xfl < it) { x_ready(true); x_issue(); }
             stamp(args, 1);                                                 // all fc1 loads issued
             // fc2: the W2 tiles do not depend on y1 -- run ahead by up to n_stages stages while the grid reduces; k
             // block kb of fc2 needs the y1 columns of wave kb * kWaves / nkb2 only.
@@ -274,40 +501,46 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // phase 3 got only 1.1 us shorter, so HBM alone is not what bounds the streaming phases; neither are the
             // activation boxes every CTA re-reads (multicasting them inside CTA pairs: no gain), nor the ring depth, nor
             // the number of W2 boxes on the SM before barrier 2 (profiles/r01g_*.txt).
-            const int first2 = it;
-            int flushed = it;          // iterations [first2, flushed) have had their y1 boxes issued
+            int flushed = it;          // fc2 iterations up to here have had their y1 boxes issued; fkb = its k block
+            int fkb = 0;               //   (kept incrementally: no divisions on this thread's critical path)
             int ready = 0;             // waves of y1 known to be complete
-            auto y1_ready = [&](int i, bool block) -> bool {   // is the y1 k block of iteration i there?
-                const int want = ((i - first2) % args.nkb2) * kWaves / args.nkb2 + 1;
+            auto y1_ready = [&](bool block) -> bool {   // is the y1 k block of iteration `flushed` there?
+                const int want = (kWaves > 1 && fkb * kWaves >= args.nkb2) ? 2 : 1;
                 while (ready < want) {
                     const unsigned long long *cnt = args.arrivals + (2 * ready + 1) * kBarLine;
                     if (block) grid_wait(cnt, bar_target);
-                    else if (!grid_poll(cnt, bar_target)) return false;
+                    else if (ready == 0 || !grid_poll(cnt, bar_target)) return false;   // no polling while running ahead
                     asm volatile("fence.proxy.async;" ::: "memory");
                     ++ready;
                     if (ready == kWaves) stamp(args, 6);                    // producer saw the last y1 barrier
                 }
                 return true;
             };
-            auto y1_issue = [&](int i) {
-                const int st = i % n_stages;
+            auto y1_issue = [&]() {    // the y1 boxes of iteration `flushed`
+                const int st = flushed % n_stages;
                 uint8_t *stg = smem + x_base + st * x_stride;
                 for (int b = 0; b < nb; ++b)
-                    tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + st, ((i - first2) % args.nkb2) * BLOCK_K, b * kXBox,
-                                kEvictLast);
+                    tma_load_2d(stg + b * kXBoxBytes, &tmap_y1, full_bar + st, fkb * BLOCK_K, b * kXBox, kEvictLast);
+                ++flushed;
+                if (++fkb == args.nkb2) fkb = 0;
             };
             for (int tile = c; tile < args.tiles2; tile += G) {
                 for (int kb = 0; kb < args.nkb2; ++kb, ++it) {
                     const int st = it % n_stages;
                     // the slot is released by the MMAs of iteration it - n_stages, which need that iteration's y1 boxes
-                    for (; flushed <= it - n_stages; ++flushed) { y1_ready(flushed, true); y1_issue(flushed); }
+                    // (and once the wait is over, every W box in the ring gets its y1 boxes at once: the MMAs must not
+                    // find the later stages empty-handed when the first one completes)
+                    if (flushed <= it - n_stages) {
+                        while (flushed <= it - n_stages) { y1_ready(true); y1_issue(); }
+                        while (flushed < it && y1_ready(false)) y1_issue();
+                    }
                     mbar_wait(empty_bar + st, (((uint32_t)(it / n_stages)) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(full_bar + st, x_bytes + kFc2N * 128);
                     tma_load_2d(smem + st * kWTileBytes, &tmap_w2, full_bar + st, kb * BLOCK_K, tile * kFc2N, kEvictFirst);
-                    for (; flushed <= it && y1_ready(flushed, false); ++flushed) y1_issue(flushed);
+                    while (flushed <= it && y1_ready(false)) y1_issue();
                 }
             }
-            for (; flushed < it; ++flushed) { y1_ready(flushed, true); y1_issue(flushed); }
+            while (flushed < it) { y1_ready(true); y1_issue(); }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -385,7 +618,32 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         float *stg = reinterpret_cast<float *>(smem + kStgOffset + ew * 2048);
         const int n_items = 2 * nb;
         int round = 0;
-        for (int w = 0; w < kWaves; ++w) {
+        if (crop && has_fc1) {
+            // ---- fused crop, bf16 operand: this CTA's quarter of the persons (rows tq, tq + 4, ...) over the columns of
+            // its K split, a chunk of cb k blocks at a time: sample into the staging area, write out as 16-byte vectors,
+            // publish on the split's chunk counter
+            const int nq = (N + kTilesPerWave - 1) / kTilesPerWave;
+            __nv_bfloat16 *stg16 = reinterpret_cast<__nv_bfloat16 *>(smem + kStgOffset);
+            const int rowlen = cb * BLOCK_K;
+            for (int ch = 0, r0 = 0; r0 < nkz; ++ch, r0 += cb) {
+                const int kA = (kb0 + r0) * BLOCK_K, kB = min((kb0 + min(nkz, r0 + cb)) * BLOCK_K, args.D);
+                crop_sample_rows<__nv_bfloat16>(args.crop, s_off, N, tq, kTilesPerWave, nq, kA, kB, stg16, rowlen, tid_e);
+                epi_bar_sync();
+                const int vec_row = (kB - kA) >> 3;                         // 16-byte vectors per row
+                for (int v = tid_e; v < nq * vec_row; v += kEpiWarps * 32) {
+                    const int pi = v / vec_row, off = v - pi * vec_row, row = tq + pi * kTilesPerWave;
+                    if (row < N)
+                        __stcg(reinterpret_cast<uint4 *>(args.crop.x_bf16 + (size_t)row * args.D + kA) + off,
+                               reinterpret_cast<const uint4 *>(stg16 + (size_t)pi * rowlen)[off]);
+                }
+                epi_bar_sync();
+                if (tid_e == 0) {
+                    grid_arrive(args.crop.xready + z * 4 + ch);
+                    stamp(args, ch == 0 ? 11 : 12);                         // first / latest chunk published
+                }
+            }
+        }
+        for (int w = 0; w < (only ? 0 : kWaves); ++w) {
             const int col0 = w * (args.hidden / kWaves);                    // first hidden unit of the wave
             if (has_fc1) {   // ---- fc1 partial sums: partial[z][person][hq*256 + m*128 + q*32 + lane]
                 const int stage = round % n_acc, hq = w * kTilesPerWave + tq;
@@ -485,6 +743,33 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int tc = m * 128 + q * 32 + lane;
                 bias[m] = (tc < kFc2N && n0 + tc < args.D) ? __ldg(args.b2 + n0 + tc) : 0.0f;
             }
+            if (crop) {
+                // ---- fused crop, fp32 residual: the tile's columns of every person, sampled while the tile's weights
+                // stream, staged and stored as 16-byte vectors where the reduce-adds below will add relu(acc + b2)
+                float *stgf = reinterpret_cast<float *>(smem + kStgOffset);
+                const int kA = n0, kB = min(n0 + kFc2N, args.D);
+                constexpr int kPass = (kEpiWarps * 2048) / (kFc2N * 4);     // 34 persons fit the staging area
+                if (tile != c) {                                            // an earlier tile's boxes may still be read
+                    if (lane == 0) tma_store_wait_all();
+                    __syncwarp();
+                    epi_bar_sync();
+                }
+                for (int r0 = 0; r0 < N; r0 += kPass) {
+                    const int rows = min(kPass, N - r0);
+                    crop_sample_rows<float>(args.crop, s_off, N, r0, 1, rows, kA, kB, stgf, kFc2N, tid_e);
+                    epi_bar_sync();
+                    const int vec_row = (kB - kA) >> 2;
+                    for (int v = tid_e; v < rows * vec_row; v += kEpiWarps * 32) {
+                        const int pi = v / vec_row, off = v - pi * vec_row;
+                        __stcg(reinterpret_cast<float4 *>(args.logits + (size_t)(r0 + pi) * args.D + kA) + off,
+                               reinterpret_cast<const float4 *>(stgf + (size_t)pi * kFc2N)[off]);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");        // generic stores before the async-proxy reduce-adds
+                    epi_bar_sync();
+                }
+                if (tid_e == 0) stamp(args, 13);                            // residual of the tile stored
+                if (only) continue;
+            }
             const int stage = round % n_acc;
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * kStageCols);
             mbar_wait(tmem_full_bar + stage, ((uint32_t)(round / n_acc)) & 1u);
@@ -545,7 +830,7 @@ struct FusedState {
     FusedMaps maps;
     float *partial;
     size_t split_stride;
-    unsigned long long *bar;   // grid barrier arrival counter
+    unsigned long long *bar;   // grid barrier arrival counters, then the chunk counters of the fused crop ([splits, 4])
     unsigned long long *trace;
     int grid, splits, rows_cap;
     const float *out_ptr;      // buffer maps.out describes (handle-owned buffers only)
@@ -559,9 +844,10 @@ int prn_fused_prepare(mpn_handle *h)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop || sms < kTilesPerWave) return MPN_OK;
-    if (cudaFuncSetAttribute(prn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(prn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel<true>, kThreads, kSmemBytes) != cudaSuccess ||
+    if (cudaFuncSetAttribute(prn_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(prn_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(prn_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel<true, true>, kThreads, kSmemBytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         snprintf(h->err, sizeof(h->err), "prn_fused_kernel cannot be made resident (smem %d)", kSmemBytes);
@@ -578,8 +864,8 @@ int prn_fused_prepare(mpn_handle *h)
     st->split_stride = (size_t)st->rows_cap * Hd;
     const uint64_t rows = (uint64_t)h->prn_ws.n_max;
     bool ok = cudaMalloc(&st->partial, (size_t)st->splits * st->split_stride * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&st->bar, 2 * kWaves * kBarLine * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMemset(st->bar, 0, 2 * kWaves * kBarLine * sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc(&st->bar, (2 * kWaves * kBarLine + 4 * st->splits) * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(st->bar, 0, (2 * kWaves * kBarLine + 4 * st->splits) * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && encode_2d(&st->maps.x, h->crops_bf16, rows, (uint64_t)D, kXBox) &&
          encode_2d(&st->maps.w1, h->W1t, (uint64_t)Hd, (uint64_t)D, kFc1N) &&
          encode_2d(&st->maps.y1, h->prn_ws.y1_bf16, rows, (uint64_t)Hd, kXBox) &&
@@ -626,11 +912,27 @@ int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int
     return MPN_OK;
 }
 
-int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s)
+// Can this call's crop_and_resize run inside the kernel (CropFuse)?  One fc1 wave, the 56 x 36 x 17 crop, at most 256 images.
+bool prn_fused_can_crop(const mpn_handle *h, int batch)
+{
+    return h->fused != nullptr && kWaves == 1 && h->cfg.crop_height == kCropH && h->cfg.crop_width == kCropW &&
+           h->cfg.num_keypoints == kCropCh && batch <= 256 && h->crops_bf16 != nullptr;
+}
+
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s,
+                     const FusedCropCall *fc)
 {
     FusedState *st = static_cast<FusedState *>(h->fused);
     if (!st) return -(int)cudaErrorInvalidValue;
     FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    if (fc) {
+        if (x_f32 != logits || !prn_fused_can_crop(h, fc->pl.B)) return -(int)cudaErrorInvalidValue;
+        a.crop.nh = fc->nh; a.crop.hh = fc->hh; a.crop.ww = fc->ww; a.crop.pl = fc->pl;
+        a.crop.x_bf16 = h->crops_bf16;
+        a.crop.xready = st->bar + 2 * kWaves * kBarLine;
+        a.crop.only = fc->only;
+    }
     a.n_dev = n_dev; a.n_host = n_host;
     a.D = h->D; a.hidden = h->cfg.prn_hidden;
     a.nkb1 = (h->D + BLOCK_K - 1) / BLOCK_K;
@@ -664,9 +966,11 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
             return -(int)cudaErrorInvalidValue;
         st->out_ptr = n_dev ? logits : nullptr;        // a caller's buffer may change size between calls: never cached
     }
-    cudaError_t e = in_place ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true>, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2,
-                                                  st->maps.out, st->maps.out16, a)
-                             : cudaLaunchKernelEx(&cfg, prn_fused_kernel<false>, st->maps.x, st->maps.w1, st->maps.y1,
+    cudaError_t e = fc ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true, true>, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2,
+                                            st->maps.out, st->maps.out16, a)
+                  : in_place ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true, false>, st->maps.x, st->maps.w1, st->maps.y1,
+                                                  st->maps.w2, st->maps.out, st->maps.out16, a)
+                             : cudaLaunchKernelEx(&cfg, prn_fused_kernel<false, false>, st->maps.x, st->maps.w1, st->maps.y1,
                                                   st->maps.w2, st->maps.out, st->maps.out16, a);
     if (e != cudaSuccess) return -(int)e;
     return 1;

@@ -333,3 +333,61 @@ def test_prn_sweep_sampled_rows(weights, n):
                              emul.reshape(-1, 56, 36, 17), f"c5 n={n}", 2 * RTOL_BF16)
     finally:
         det.close()
+
+
+# ------------------------------------------------------------------- crop_and_resize inside the single-kernel PRN (CropFuse)
+@pytest.mark.parametrize("key,batch,max_boxes", [("tiny", None, None), ("c1", None, None), ("c2", 8, None), ("c2", 3, None),
+                                                 ("c3", 2, 128)])
+def test_fused_crop_equals_the_crop_kernel_bit_for_bit(weights, monkeypatch, key, batch, max_boxes):
+    """MPN_FUSE_CROP=1: calls that fit the single-kernel PRN (capacity <= 256 persons) sample their crops inside it
+    (create_pb.py:106-109 fused into the producer of fc1 and the residual of fc2, north_star) and never launch the crop
+    kernel.  The crops it leaves in memory (bf16 operand, fp32 residual: skip bit 64 stops the kernel after sampling), the
+    flat person list and every output of the whole call must equal the crop-kernel path bit for bit -- that path is the
+    one checked against the oracle above."""
+    wl = synthetic.WORKLOADS[key]
+    B = wl.batch if batch is None else batch
+    inp = synthetic.make_inputs(wl, batch=B)
+    kw = dict(prn_mode="bf16", prn_modes_allocated=("bf16",))
+    if max_boxes is not None:
+        kw["max_boxes"] = max_boxes
+    res = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("MPN_FUSE_CROP", fuse)
+        det = make_det(weights, wl, B, **kw)
+        try:
+            dev_in = [_cuda(inp[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")]
+            det.debug_skip((64 | 32) if fuse == "1" else (16 | 32))
+            out = det.run_device(*dev_in)
+            torch.cuda.synchronize()
+            det.debug_skip(0)
+            N = int(out["person_offsets"].cpu().numpy()[-1])
+            r = {"N": N,
+                 "crops_f32": det.debug_fetch("crops_f32").reshape(-1, 56 * 36 * 17)[:N].cpu().numpy().copy(),
+                 "crops_bf16": det.debug_fetch("crops_bf16").reshape(-1, 56 * 36 * 17)[:N].view(torch.int16).cpu().numpy().copy(),
+                 "person_box": det.debug_fetch("person_box").cpu().numpy().reshape(-1, 4)[:N].copy(),
+                 "person_image": det.debug_fetch("person_image").cpu().numpy()[:N].copy()}
+            for rep in range(2):                       # second call = graph replay
+                out = det.run_device(*dev_in)
+            torch.cuda.synchronize()
+            r["out"] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+            r["launches"] = det.launch_count()[0] if hasattr(det, "launch_count") else None
+            res.append(r)
+        finally:
+            det.close()
+    a, b = res
+    assert a["N"] == b["N"] and a["N"] > 0
+    assert B * (max_boxes or wl.max_detections) <= 256, "the case must fit the single-kernel PRN"
+    N = a["N"]
+    assert_bits(b["person_box"], a["person_box"], "person list: boxes")
+    assert np.array_equal(b["person_image"], a["person_image"]), "person list: box_ind"
+    assert_bits(b["crops_f32"], a["crops_f32"], "fp32 crops sampled inside the PRN kernel")
+    assert np.array_equal(b["crops_bf16"], a["crops_bf16"]), "bf16 crops sampled inside the PRN kernel"
+    for k in a["out"]:
+        rows = N if k in ("keypoint_scores", "keypoint_positions") else None
+        ga, gb = a["out"][k][:rows], b["out"][k][:rows]
+        if ga.dtype == np.float32:
+            assert_bits(gb, ga, k)
+        else:
+            assert np.array_equal(gb, ga), k
+    if a["launches"] is not None:
+        assert b["launches"] == a["launches"] - 1, (a["launches"], b["launches"])      # no crop kernel
