@@ -43,7 +43,7 @@ def _stale(target, deps):
 
 
 # Variant builds for measurements (never loaded unless MPN_LIB points at them): name -> extra nvcc flags
-VARIANTS = {"waves1": ["-DMPN_FC1_WAVES=1"], "waves2": ["-DMPN_FC1_WAVES=2"]}
+VARIANTS = {"waves1": ["-DMPN_FC1_WAVES=1"], "waves2": ["-DMPN_FC1_WAVES=2"], "rankcut2t": ["-DMPN_NMS_RANK_CUT=4096"]}
 
 
 def build_variant(name, force=False):

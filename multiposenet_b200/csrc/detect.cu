@@ -188,6 +188,13 @@ template <int T>
 __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, const DetectArgs a)
 {
     constexpr int kNmsThreads = T, kChunk = T, kMaskWords = T / 32, kRankSortCap = 2 * T;
+    // The one-pass rank sort costs C * C / 2T key comparisons per thread: past one key per thread (~3 k instructions per
+    // thread, all 32 warps of the SM) the bucketed sort below is cheaper, whatever the count (MPN_NMS_RANK_CUT for measurements).
+#ifdef MPN_NMS_RANK_CUT
+    constexpr int kRankCut = MPN_NMS_RANK_CUT < kRankSortCap ? MPN_NMS_RANK_CUT : kRankSortCap;
+#else
+    constexpr int kRankCut = T;
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem<T> &sm = *reinterpret_cast<NmsSmem<T> *>(smem_raw);
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
         __syncthreads();
         if (tid < C) sm.sorted[sm.kept_local[tid]] = sm.keys[tid];
         keys = sm.sorted;
-    } else if (C <= kRankSortCap) {
+    } else if (C <= kRankCut) {
         for (int i = tid; i < C; i += kNmsThreads) sm.keys[i] = gkeys[i];
         if (tid == 0 && (C & 1)) sm.keys[C] = 0ULL;    // zero pad: never greater than a real key (score bits > 0)
         __syncthreads();
