@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libmpn_b200.so")
-SOURCES = ["api.cu", "detect.cu", "heatmap.cu", "kpdecode.cu", "prn_simt.cu", "prn_tcgen05.cu", "prn_fused.cu", "prn_big.cu", "math_test.cu"]
+SOURCES = ["api.cu", "detect.cu", "heatmap.cu", "kpdecode.cu", "prn_simt.cu", "prn_tcgen05.cu", "prn_fused.cu", "prn_split3.cu", "prn_big.cu", "math_test.cu"]
 HEADERS = ["common.cuh", "handle.cuh", "mpn_math.cuh", "tcgen05_utils.cuh", "bulk_copy.cuh", os.path.join("..", "..", "include", "mpn_b200.h")]
 
 NVCC_FLAGS = [

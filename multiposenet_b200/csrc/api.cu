@@ -212,7 +212,17 @@ int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const
     w.W1 = h->W1; w.b1 = h->b1; w.W2 = h->W2; w.b2 = h->b2; w.W1t = h->W1t; w.W2t = h->W2t;
     if (mode == MPN_PRN_FP32) {
         if (!(h->cfg.prn_modes & 1)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the fp32 PRN");
-        return launched(h, launch_prn_fp32(w, h->prn_ws, x_f32, n_dev, n_host, n_max, logits, s), first, "prn fp32");
+        // <= 240 persons: the fp32-accurate tensor-core kernel (prn_split3.cu: three bf16 parts per number, one pass over
+        // the weights per group of 80 persons); more: the SIMT kernels.  The count is only known on the device: both are launched when the call's
+        // capacity exceeds 240, and each exits at once outside its regime.
+        int skip_le = 0;
+        if (h->split3) {
+            int rc = launched(h, launch_prn_split3(h, x_f32, n_dev, n_host, n_max, logits, s), first, "prn split3");
+            if (rc || n_max <= kPrnSplit3MaxRows) return rc;
+            first = false;
+            skip_le = kPrnSplit3MaxRows;
+        }
+        return launched(h, launch_prn_fp32(w, h->prn_ws, x_f32, n_dev, n_host, n_max, logits, skip_le, s), first, "prn fp32");
     }
     if (!(h->cfg.prn_modes & 2)) return fail(h, MPN_ERR_UNSUPPORTED, "handle was created without the bf16 PRN");
     // <= 256 persons: one persistent kernel (prn_fused.cu); above: the tiled GEMM kernels.  The person count is only
@@ -419,6 +429,14 @@ int mpn_create(const mpn_config *cfg, mpn_handle **out)
             return rc;
         }
     }
+    if (cfg->prn_modes & 1) {
+        const int rc = prn_split3_prepare(h);
+        if (rc != MPN_OK) {
+            snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+            mpn_destroy(h);
+            return rc;
+        }
+    }
     *out = h;
     return MPN_OK;
 }
@@ -430,6 +448,7 @@ void mpn_destroy(mpn_handle *h)
     cudaDeviceSynchronize();
     prn_bf16_release(h);
     prn_fused_release(h);
+    prn_split3_release(h);
     prn_big_release(h);
     void *ptrs[] = {h->cand_keys, h->cand_count, h->person_box, h->person_img, h->person_offsets,
                     h->kh_ws, h->nh_ws, h->minmax_ws, h->hm_partial, h->hm_partial2, h->hm_counter, h->nms_trace, h->crops_f32, h->logits, h->crops_bf16, h->W1, h->b1, h->W2, h->b2, h->W1t,
@@ -490,6 +509,7 @@ int mpn_set_prn_weights(mpn_handle *h, const float *W1, const float *b1, const f
         launch_transpose_to_bf16(dW1, (int)D, (int)Hd, h->W1t, s);
         launch_transpose_to_bf16(dW2, (int)Hd, (int)D, h->W2t, s);
     }
+    if (h->cfg.prn_modes & 1) prn_split3_set_weights(h, dW1, dW2, s);
     MPN_CUDA(h, cudaStreamSynchronize(s));
     if (temp) { cudaFree(dW1); cudaFree(dW2); }
     MPN_CUDA(h, cudaGetLastError());

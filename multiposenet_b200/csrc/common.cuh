@@ -14,6 +14,8 @@ constexpr int kMaxShapes = MPN_MAX_ANCHOR_SHAPES;
 constexpr int kSortSmemCap = 8192;      // candidates per image sorted in shared memory; above: global scratch
 constexpr int kMaxDetCap = 1024;        // kept boxes staged in shared memory
 constexpr int kPrnFusedMaxRows = 256;   // persons per call handled by the single-kernel PRN (prn_fused.cu)
+constexpr int kPrnSplit3GroupRows = 80; // persons per launch of the fp32-accurate tensor-core PRN (prn_split3.cu)
+constexpr int kPrnSplit3MaxRows = 240;  //   ... and per call (three launches); more: the SIMT kernels
 
 // Everything the kernels need to rebuild anchor `a` from its index (detector/anchor_generator.py:53-116)
 // without an anchor tensor in HBM.  Passed by value (~1.3 KB of kernel parameters).
@@ -167,8 +169,9 @@ struct PrnWorkspace {
     __nv_bfloat16 *y1_bf16;  // [n_max_pad, hidden]
     int n_max;
 };
+// skip_le: the kernels exit at once when the person count is <= skip_le (prn_split3.cu handles those)
 int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x, const int *n_dev, int n_host,
-                    int n_max, float *logits, cudaStream_t s);
+                    int n_max, float *logits, int skip_le, cudaStream_t s);
 // skip_le: the launched kernels exit at once when the person count is <= skip_le (the fused kernel handles those)
 int launch_prn_bf16(const PrnWeights &w, const PrnWorkspace &ws, const float *x_f32, const __nv_bfloat16 *x_bf16,
                     const int *n_dev, int n_host, int n_max, float *logits, void *tmaps, int skip_le, cudaStream_t s);

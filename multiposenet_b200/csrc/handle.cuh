@@ -74,6 +74,7 @@ struct mpn_handle {
     mpn::PrnWorkspace prn_ws;
     void *tmaps;            // opaque: prn_tcgen05.cu
     void *fused;            // opaque: prn_fused.cu (NULL when the shape is not covered)
+    void *split3;           // opaque: prn_split3.cu (fp32 mode on the tensor cores, <= 80 persons; NULL: SIMT kernels only)
     void *big;              // opaque: prn_big.cu (NULL when the shape is not covered or the capacity is <= 256 persons)
     bool have_weights;
     int decode_clusters;    // keypoint decode: clusters resident at once (kpdecode_prepare)
@@ -101,6 +102,10 @@ int prn_big_prepare(mpn_handle *h);    // prn_big.cu: persistent tcgen05 GEMMs f
 void prn_big_release(mpn_handle *h);
 int launch_prn_big(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, int n_max, float *logits, int skip_le,
                    cudaStream_t s);
+int prn_split3_prepare(mpn_handle *h); // prn_split3.cu: fp32-accurate PRN on the tensor cores (three bf16 parts per number)
+void prn_split3_release(mpn_handle *h);
+int prn_split3_set_weights(mpn_handle *h, const float *dW1, const float *dW2, cudaStream_t s);
+int launch_prn_split3(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, int n_max, float *logits, cudaStream_t s);
 int prn_fused_prepare(mpn_handle *h);  // prn_fused.cu: persistent single-kernel PRN for <= kPrnFusedMaxRows persons
 void prn_fused_release(mpn_handle *h);
 int prn_fused_trace(mpn_handle *h, int enable, unsigned long long *host_out, int capacity, int *grid_out);

@@ -27,13 +27,13 @@ __global__ void __launch_bounds__(kThreads) sgemm_kernel(const float *__restrict
                                                          const int *__restrict__ m_dev, const int m_host,
                                                          const int k_per_split, const float *__restrict__ bias,
                                                          const float *__restrict__ residual, float *__restrict__ C,
-                                                         const size_t split_stride)
+                                                         const size_t split_stride, const int skip_le)
 {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int M = m_dev ? *m_dev : m_host;
     const int m0 = blockIdx.y * BM;
-    if (m0 >= M) return;
+    if (m0 >= M || M <= skip_le) return;
     const int n0 = blockIdx.x * BN;
     const int k_begin = blockIdx.z * k_per_split, k_end = k_begin + k_per_split;
     const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
@@ -158,7 +158,7 @@ int pick_splits(int k_slabs, int ctas_without_split)
 }  // namespace
 
 int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x, const int *n_dev, int n_host,
-                    int n_max, float *logits, cudaStream_t s)
+                    int n_max, float *logits, int skip_le, cudaStream_t s)
 {
     if (n_max <= 0) return 0;
     const int D = w.D, Hd = w.hidden;
@@ -173,16 +173,16 @@ int launch_prn_fp32(const PrnWeights &w, const PrnWorkspace &ws, const float *x,
         dim3 grid(Hd / BN, m_tiles, splits);
         prof_mark(s, "prn_fp32_fc1");
         sgemm_kernel<EPI_PARTIAL><<<grid, kThreads, 0, s>>>(x, D, w.W1, Hd, n_dev, n_host, D / splits, nullptr,
-                                                            nullptr, ws.partial, split_stride);
+                                                            nullptr, ws.partial, split_stride, skip_le);
         ++launches;
-        launches += launch_fc1_reduce(ws.partial, splits, split_stride, w.b1, Hd, n_dev, n_host, n_max, ws.y1, nullptr, 0, s);
+        launches += launch_fc1_reduce(ws.partial, splits, split_stride, w.b1, Hd, n_dev, n_host, n_max, ws.y1, nullptr, skip_le, s);
     }
     // fc2 + bias + ReLU + residual
     {
         dim3 grid((D + BN - 1) / BN, m_tiles, 1);
         prof_mark(s, "prn_fp32_fc2");
         sgemm_kernel<EPI_BIAS_RELU_RESIDUAL><<<grid, kThreads, 0, s>>>(ws.y1, Hd, w.W2, D, n_dev, n_host, Hd, w.b2, x,
-                                                                       logits, 0);
+                                                                       logits, 0, skip_le);
         ++launches;
     }
     return launches;

@@ -320,6 +320,41 @@ def test_prn_fp32_within_1e4(det6, prn_weights, n):
     np.testing.assert_allclose(got, want, rtol=RTOL_FP32, atol=RTOL_FP32 * np.abs(want).max())
 
 
+@pytest.mark.parametrize("n", [1, 16, 17, 78, 80, 81, 200, 240, 250])
+def test_prn_fp32_on_tensor_cores_is_fp32_accurate(prn_weights, monkeypatch, n):
+    """fp32 mode, <= 240 persons: prn_split3.cu (every number as three bf16 parts, fp32 accumulation in tensor memory, one
+    launch per group of 80 persons) must be as good as the SIMT fp32 kernels it replaces there (detector/prn.py:15-25):
+    within 1e-5 of the fp64-accumulating oracle relative to the output scale (the north_star bar for fp32 is 1e-4), and
+    within 1e-5 of the SIMT result.  250 persons take the SIMT kernels (both are launched, each exits outside its regime)."""
+    from multiposenet_b200 import Detector, DetectorConfig
+    x = synthetic.make_crops(n, seed=500 + n)
+    want = oracle.prn(x, *prn_weights, mode=0)
+    got = {}
+    for simt in (False, True):
+        if simt:
+            monkeypatch.setenv("MPN_FP32_SIMT", "1")
+        else:
+            monkeypatch.delenv("MPN_FP32_SIMT", raising=False)
+        det = Detector(prn_weights, DetectorConfig(max_batch=8, max_boxes=32, prn_mode="fp32", prn_modes_allocated=("fp32",)))
+        try:
+            before = det.launch_count()[1]
+            for _ in range(2):
+                out = det.prn(_cuda(x), "fp32")
+            got[simt] = out.cpu().numpy()
+            launches = (det.launch_count()[1] - before) // 2
+        finally:
+            det.close()
+        if not simt:
+            assert launches == (2 * ((n + 79) // 80) if n <= 240 else 2 * 3 + 3), launches   # parts + kernel per group (+ SIMT)
+        else:
+            assert launches == 3, launches
+    scale = np.abs(want).max()
+    err_tc, err_simt = np.abs(got[False] - want).max() / scale, np.abs(got[True] - want).max() / scale
+    print(f"n={n}: max |error| / scale: tensor-core fp32 {err_tc:.2e}, SIMT fp32 {err_simt:.2e}")
+    assert err_tc < 1e-5 and err_simt < 1e-5
+    assert np.abs(got[False] - got[True]).max() / scale < 1e-5
+
+
 @pytest.mark.parametrize("n", [1, 5, 130, 256, 300, 600])
 def test_prn_bf16_tcgen05_within_1e2_and_close_to_bf16_oracle(det6, prn_weights, n):
     x = synthetic.make_crops(n, seed=31 + n)
