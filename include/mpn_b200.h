@@ -49,7 +49,8 @@ typedef enum mpn_status {
 } mpn_status;
 
 typedef enum mpn_prn_mode {
-    MPN_PRN_FP32 = 0,   /* fp32 weights and activations, FFMA (parity mode, 1e-4) */
+    MPN_PRN_FP32 = 0,   /* fp32-accurate (parity mode, 1e-4; measured ~1e-6): <= 240 persons per call on the tensor cores with every
+                         * number as three bf16 parts and fp32 accumulation (prn_split3.cu), more persons on FFMA (prn_simt.cu) */
     MPN_PRN_BF16 = 1    /* bf16 weights and activations on tcgen05 tensor cores, fp32 accumulate (1e-2) */
 } mpn_prn_mode;
 
