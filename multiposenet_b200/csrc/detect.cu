@@ -69,15 +69,41 @@ __device__ __forceinline__ float4 decode_box(const Anchor an, const float4 code,
     return make_float4(clip01(fsub(cy, hh)), clip01(fsub(cx, hw)), clip01(fadd(cy, hh)), clip01(fadd(cx, hw)));
 }
 
-__device__ __forceinline__ void push_candidate(const DetectArgs &a, int img, int anchor, float logit)
+// A confident anchor's sort key (score bits << 32 | ~anchor: a descending sort gives score desc, anchor asc), or 0 when the
+// anchor does not pass (a score == thr passes nms.py:30 but can never be selected by the NMS op: strict >).
+__device__ __forceinline__ unsigned long long candidate_key(const DetectArgs &a, int anchor, float logit)
 {
     const float s = exact_sigmoidf(logit);
-    if (s > a.thr) {   // == thr passes nms.py:30 but can never be selected by the NMS op (strict >)
-        const int slot = atomicAdd(a.cand_count + img, 1);
-        const unsigned long long key =
-            ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)anchor);
-        a.cand_keys[(size_t)img * a.key_cap + slot] = key;
+    return s > a.thr ? ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)anchor) : 0ULL;
+}
+
+// Appending the candidates of a CTA to their images' lists: ONE global atomic per CTA and image.  The slots inside the CTA
+// come from a shared-memory counter; the order of a list does not matter (it is sorted, the keys are distinct).  One
+// global atomic per candidate serialises on the image's counter: 2 100 candidates per image cost 47 us of a crowded call.
+// `which` = the candidate's image minus the CTA's first image (a CTA touches at most kCandImgs images).
+constexpr int kCandImgs = 2;
+struct CandSlots { int cnt[kCandImgs], base[kCandImgs]; };
+
+template <int PER>
+__device__ __forceinline__ void append_candidates(const DetectArgs &a, CandSlots &sm, const int img0, const int n_imgs,
+                                                  const unsigned long long (&key)[PER], const int (&which)[PER])
+{
+    // (sm.cnt zeroed and a __syncthreads() passed by the caller)
+    int slot[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        slot[j] = -1;
+        if (key[j] && which[j] < kCandImgs) slot[j] = atomicAdd(&sm.cnt[which[j]], 1);
+        else if (key[j])                               // anchor sets so small that a CTA spans more images: one by one
+            a.cand_keys[(size_t)(img0 + which[j]) * a.key_cap + atomicAdd(a.cand_count + img0 + which[j], 1)] = key[j];
     }
+    __syncthreads();
+    if (threadIdx.x < n_imgs && sm.cnt[threadIdx.x] > 0)
+        sm.base[threadIdx.x] = atomicAdd(a.cand_count + img0 + threadIdx.x, sm.cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (slot[j] >= 0) a.cand_keys[(size_t)(img0 + which[j]) * a.key_cap + sm.base[which[j]] + slot[j]] = key[j];
 }
 
 __global__ void anchors_kernel(const AnchorTable t, float4 *out)
@@ -88,50 +114,67 @@ __global__ void anchors_kernel(const AnchorTable t, float4 *out)
     out[a] = make_float4(an.ymin, an.xmin, an.ymax, an.xmax);
 }
 
-// Concatenated [B, A] logits, 4 per thread as one 16-byte load over the flat array.
+// Concatenated [B, A] logits, 4 per thread as one 16-byte load over the flat array (A >= 1024: the 1024 elements of a CTA
+// touch at most two images; smaller anchor sets still work, see append_candidates).
 __global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a, const int A, const long long total,
                                                               const int vec_ok)
 {
+    __shared__ CandSlots sm;
     pdl_trigger();
+    if (threadIdx.x < kCandImgs) sm.cnt[threadIdx.x] = 0;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long e0 = t * 4;
-    if (e0 >= total) return;
+    const int img0 = (int)(((long long)blockIdx.x * blockDim.x * 4) / A);
     float v[4];
-    int n = 4;
-    if (vec_ok && e0 + 4 <= total) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(a.cls) + t);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-        n = (int)min(4LL, total - e0);
+    int n = 0;
+    if (e0 < total) {
+        n = 4;
+        if (vec_ok && e0 + 4 <= total) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(a.cls) + t);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            n = (int)min(4LL, total - e0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (j < n) ? __ldg(a.cls + e0 + j) : -__int_as_float(0x7f800000);
+            for (int j = 0; j < 4; ++j) v[j] = (j < n) ? __ldg(a.cls + e0 + j) : -__int_as_float(0x7f800000);
+        }
     }
-    if (!((v[0] > a.pre_thr) | (v[1] > a.pre_thr) | (v[2] > a.pre_thr) | (v[3] > a.pre_thr))) return;
+    unsigned long long key[4] = {0ULL, 0ULL, 0ULL, 0ULL};
+    int which[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (j < n && v[j] > a.pre_thr) {
             const long long e = e0 + j;
             const int img = (int)(e / A);
-            push_candidate(a, img, (int)(e - (long long)img * A), v[j]);
+            key[j] = candidate_key(a, (int)(e - (long long)img * A), v[j]);
+            which[j] = img - img0;
         }
     }
+    __syncthreads();
+    append_candidates<4>(a, sm, img0, min(kCandImgs, a.B - img0), key, which);
 }
 
 // Per-level NCHW logits [B, n_loc, gh, gw]: threads walk memory order, anchor index = off + (y*gw+x)*n_loc + k.
 __global__ void __launch_bounds__(256) candidates_nchw_kernel(const AnchorTable t, const DetectArgs a)
 {
+    __shared__ CandSlots sm;
     pdl_trigger();
+    if (threadIdx.x < kCandImgs) sm.cnt[threadIdx.x] = 0;
     const int img = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;   // position inside the image's concatenated levels
-    if (e >= t.num_anchors) return;
-    const int l = level_of(t, e);
-    const int r = e - t.off[l];
-    const int plane = t.gh[l] * t.gw[l];
-    const float v = __ldg(a.lv.cls[l] + (size_t)img * plane * t.n_loc + r);
-    if (v > a.pre_thr) {
-        const int k = r / plane, loc = r - k * plane;
-        push_candidate(a, img, t.off[l] + loc * t.n_loc + k, v);
+    unsigned long long key[1] = {0ULL};
+    const int which[1] = {0};
+    if (e < t.num_anchors) {
+        const int l = level_of(t, e);
+        const int r = e - t.off[l];
+        const int plane = t.gh[l] * t.gw[l];
+        const float v = __ldg(a.lv.cls[l] + (size_t)img * plane * t.n_loc + r);
+        if (v > a.pre_thr) {
+            const int k = r / plane, loc = r - k * plane;
+            key[0] = candidate_key(a, t.off[l] + loc * t.n_loc + k, v);
+        }
     }
+    __syncthreads();
+    append_candidates<1>(a, sm, img, 1, key, which);
 }
 
 __device__ __forceinline__ float4 load_code(const AnchorTable &t, const DetectArgs &a, int img, int anchor, int l,
