@@ -93,8 +93,9 @@ def parse_args():
                          "(BASELINE configs[3]: 1024x1024, 64 images over 2/4/8 GPUs)")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="the K-step timed block is repeated until this much device time has been measured")
-    ap.add_argument("--lanes", type=int, default=3,
-                    help="Detector handles / CUDA streams fed round-robin in the device-resident leg (DetectorLanes)")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="Detector handles / CUDA streams fed round-robin in the device-resident leg (DetectorLanes); "
+                         "measured at c2 (profiles/r02w_lanes.txt): 1 / 2 / 3 / 4 lanes = 79.9 / 73.5 / 79.1 / 75.5 us per batch")
     return ap.parse_args()
 
 

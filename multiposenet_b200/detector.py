@@ -550,7 +550,7 @@ class DetectorLanes:
     CUDA stream, fed round-robin.  Calls of neighbouring batches overlap: the latency-bound front half of one call
     (candidate scan, sort / NMS, heatmap pass) and its keypoint decode run beside another call's kernels instead of
     leaving the device to one short grid at a time.  The PRN kernel owns every SM while it runs, so the gain is bounded by
-    the time of the other six kernels (c2, per batch: 88.1 us alone, 81.6 with 2 lanes, 78.4 with 3, 78.1 with 6;
+    the time of the other six kernels (c2, per batch, round 2: 79.9 us alone, 73.5 with 2 lanes, 79.1 with 3, 75.5 with 4;
     tools/two_streams.py).  Every lane is an
     independent handle (own workspace and weight copy, 0.3 GB each), so results are those of a lone Detector, bit for
     bit; a handle is not re-entrant (include/mpn_b200.h), the lanes are what makes concurrent calls legal."""

@@ -29,6 +29,9 @@ if has s; then
   python tools/prn_sweep.py 16 78 256 1000 10000 30000 100000 > $O/${T}_prn_sweep.txt 2>&1
   python tools/decode_bench.py 78 600 2801 10000 > $O/${T}_decode_bench.txt 2>&1
   python tools/two_streams.py c2 1 2 3 4 > $O/${T}_lanes.txt 2>&1
+  { echo "== crop_and_resize inside the PRN kernel (MPN_FUSE_CROP=1)"; MPN_FUSE_CROP=1 python tools/two_streams.py c2 1 3 2>&1 | tail -2;
+    MPN_FUSE_CROP=1 python tools/fused_trace.py c2 2>&1 | tail -17; echo "== default"; python tools/fused_trace.py c2 2>&1 | tail -12;
+    echo "== sort / NMS phases"; python tools/nms_trace.py c2 2>&1 | tail -7; python tools/nms_trace.py c3 2>&1 | tail -7; } > $O/${T}_traces.txt 2>&1
 fi
 if has n; then
   # ncu: only after the same command has exited 0 without it
