@@ -93,9 +93,11 @@ def parse_args():
                          "(BASELINE configs[3]: 1024x1024, 64 images over 2/4/8 GPUs)")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="the K-step timed block is repeated until this much device time has been measured")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=0,
                     help="Detector handles / CUDA streams fed round-robin in the device-resident leg (DetectorLanes); "
-                         "measured at c2 (profiles/r02w_lanes.txt): 1 / 2 / 3 / 4 lanes = 79.9 / 73.5 / 79.1 / 75.5 us per batch")
+                         "0 = what was measured best: 2 for calls of latency-bound kernels (c1, c2; c2 with 1 / 2 / 3 / 4 lanes: "
+                         "79.9 / 73.5 / 79.1 / 75.5 us per batch, profiles/r02w_lanes.txt), 3 for crowded / large calls (c3: 840 / "
+                         "854 / 812 us with 1 / 2 / 3; c4: 421 / 427 / 401)")
     return ap.parse_args()
 
 
@@ -319,7 +321,7 @@ def main():
     K, Wm = args.steps, max(args.warmup, 3)
     B = batch_per_gpu(wl, args)
     weights = synthetic.make_prn_weights()
-    n_lanes = max(1, args.lanes)
+    n_lanes = args.lanes if args.lanes > 0 else (2 if wl.batch * wl.max_detections <= 256 else 3)
     lanes = DetectorLanes(weights, DetectorConfig(
         max_batch=B, max_height=wl.height, max_width=wl.width, max_boxes=wl.max_detections,
         score_threshold=wl.score_threshold, iou_threshold=wl.iou_threshold, scale_multipliers=wl.multipliers,

@@ -229,7 +229,7 @@ int do_prn(mpn_handle *h, const float *x_f32, const __nv_bfloat16 *x_bf16, const
     // known on the device, so when the call's capacity exceeds 256 both are launched and each exits at once outside
     // its regime.
     if (h->fused) {
-        int rc = launched(h, launch_prn_fused(h, x_f32, n_dev, n_host, logits, s, fc), first, "prn fused");
+        int rc = launched(h, launch_prn_fused(h, x_f32, n_dev, n_host, n_max, logits, s, fc), first, "prn fused");
         if (rc || n_max <= kPrnFusedMaxRows) return rc;
         first = false;
     }

@@ -118,6 +118,6 @@ struct FusedCropCall {
     int only;               // development aid: sample the crops (bf16 and fp32) and stop
 };
 bool prn_fused_can_crop(const mpn_handle *h, int batch);
-int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s,
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, int n_max, float *logits, cudaStream_t s,
                      const FusedCropCall *fc = nullptr);
 }

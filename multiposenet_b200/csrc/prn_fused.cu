@@ -109,6 +109,9 @@ struct FusedArgs {
     CropFuse crop;
     const int *n_dev;
     int n_host;
+    int early_boxes;         // W1 boxes requested before the person count is known: kEarly, or 0 when the call's capacity
+                             // exceeds this kernel's regime (crowded calls: it mostly exits, and 14 MB of W1 would be
+                             // fetched and drained for nothing -- 10 us of a c3 / c4 call)
     int D, hidden;
     int nkb1;                // k blocks of fc1 (ceil(D / 64))
     int nkb2;                // k blocks of fc2 (hidden / 64)
@@ -325,6 +328,13 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 {
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
+    if (args.early_boxes == 0 && !(kCrop && args.crop.nh != nullptr)) {
+        // the call's capacity exceeds this kernel's regime: it will most likely exit, so look at the count first, before
+        // tensor memory, barriers and weight boxes are set up for nothing
+        pdl_wait();
+        const int n = args.n_dev ? *args.n_dev : args.n_host;
+        if (!(n > 0 && n <= kPrnFusedMaxRows)) return;
+    }
     const int G = gridDim.x, c = blockIdx.x;
     // this launch's barrier base; read before this CTA can possibly have arrived anywhere
     const unsigned long long bar_base = (ld_acquire_u64(args.arrivals) / (unsigned long long)G) * (unsigned long long)G;
@@ -366,7 +376,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // transaction bytes now and the producer's arrival (with the activation bytes) after the wait.
     int early = 0;
     if (threadIdx.x == 0 && has_fc1) {
-        early = min(kEarly, kb1 - kb0);
+        early = min(args.early_boxes, kb1 - kb0);
         for (int i = 0; i < early; ++i) {
             mbar_expect_tx(full_bar + i, kFc1N * 128);
             tma_load_2d(smem + i * kWTileBytes, &tmap_w1, full_bar + i, (kb0 + i) * BLOCK_K, tq * kFc1N, kEvictFirst);
@@ -919,7 +929,7 @@ bool prn_fused_can_crop(const mpn_handle *h, int batch)
            h->cfg.num_keypoints == kCropCh && batch <= 256 && h->crops_bf16 != nullptr;
 }
 
-int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, float *logits, cudaStream_t s,
+int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_host, int n_max, float *logits, cudaStream_t s,
                      const FusedCropCall *fc)
 {
     FusedState *st = static_cast<FusedState *>(h->fused);
@@ -934,6 +944,7 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
         a.crop.only = fc->only;
     }
     a.n_dev = n_dev; a.n_host = n_host;
+    a.early_boxes = n_max <= kPrnFusedMaxRows ? kEarly : 0;
     a.D = h->D; a.hidden = h->cfg.prn_hidden;
     a.nkb1 = (h->D + BLOCK_K - 1) / BLOCK_K;
     a.nkb2 = h->cfg.prn_hidden / BLOCK_K;

@@ -125,6 +125,11 @@ prn_split3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 {
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
+    if (args.row0 > 0) {   // a later group of the call: mostly empty, so look at the count before anything is set up
+        pdl_wait();
+        const int n = args.n_dev ? *args.n_dev : args.n_host;
+        if (!(n > args.row0 && n <= kRows3 * kGroups3)) return;
+    }
     const int G = gridDim.x, c = blockIdx.x;
     const unsigned long long bar_target =
         (ld_acquire_u64(args.arrivals) / (unsigned long long)G) * (unsigned long long)G + (unsigned long long)G;
@@ -163,7 +168,8 @@ prn_split3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int t0 = kb0 / args.third1;                    // the third the split starts in: 3 - t0 variants are live in it
 
     int early = 0;
-    if (threadIdx.x == 0 && has_fc1) {                   // weight boxes that do not depend on the crops
+    if (threadIdx.x == 0 && has_fc1 && args.row0 == 0) { // weight boxes that do not depend on the crops (first group only:
+                                                         // the later groups of a call are mostly empty and exit)
         early = min(kEarly, kb1 - kb0);
         for (int i = 0; i < early; ++i) {
             mbar_expect_tx(full_bar + i, kFc1N * 128);
