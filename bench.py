@@ -550,6 +550,22 @@ def main():
             det.debug_skip(0)
             launch_ms = p0.elapsed_time(p1) / reps
             timing = f"CUDA events around {reps} graph replays that contain only this kernel (all other stages skipped)"
+            # for explanation only: the kernel's own duration INSIDE whole calls, from its globaltimer stamps (first CTA
+            # past its prologue -> last logit stored; mpn_debug_fused_trace) -- what a replay adds to that is launch latency
+            try:
+                det.fused_trace(True)
+                spans = []
+                with torch.cuda.stream(side):
+                    for i in range(3 * m_sets):
+                        dev_step(i % m_sets)
+                        side.synchronize()
+                        tr = det.fused_trace(True).astype("int64")
+                        if (tr[:, 10] > 0).any():
+                            spans.append((tr[:, 10].max() - tr[:, 0][tr[:, 0] > 0].min()) / 1e6)
+                det.fused_trace(False)
+                in_kernel_ms = float(sorted(spans)[len(spans) // 2]) if spans else None
+            except Exception:
+                in_kernel_ms = None
         ach = ab / launch_ms / 1e6
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": which,
@@ -558,6 +574,9 @@ def main():
                     "avg_launch_ms": round(launch_ms, 5), "timing": timing,
                     "avg_launch_ms_profiling_pass": round(mean[top], 5),
                     "persons_per_batch": persons, "candidates_per_batch": n_cand}
+        if top == "prn_fused" and in_kernel_ms:
+            roofline["in_kernel_ms_inside_a_call"] = round(in_kernel_ms, 5)
+            roofline["frac_in_kernel"] = round(ab / in_kernel_ms / 1e6 / hbm_peak, 4)
 
     # ---- leg 4: CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------
     cpu = None
