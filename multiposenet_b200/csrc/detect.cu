@@ -114,43 +114,55 @@ __global__ void anchors_kernel(const AnchorTable t, float4 *out)
     out[a] = make_float4(an.ymin, an.xmin, an.ymax, an.xmax);
 }
 
-// Concatenated [B, A] logits, 4 per thread as one 16-byte load over the flat array (A >= 1024: the 1024 elements of a CTA
-// touch at most two images; smaller anchor sets still work, see append_candidates).
+// Concatenated [B, A] logits: kCandVec 16-byte loads per thread over the flat array (a CTA covers
+// 256 * 4 * kCandVec consecutive elements: at most two images when A >= that; smaller anchor sets still work, see
+// append_candidates).  A CTA without a confident anchor -- almost all of them -- leaves after one barrier.
+constexpr int kCandVec = 1;      // (4 loads per thread and a quarter of the CTAs: 9.5 -> 13.2 us at c2, 13.4 -> 20.0 at c3)
 __global__ void __launch_bounds__(256) candidates_flat_kernel(const DetectArgs a, const int A, const long long total,
                                                               const int vec_ok)
 {
     __shared__ CandSlots sm;
     pdl_trigger();
     if (threadIdx.x < kCandImgs) sm.cnt[threadIdx.x] = 0;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e0 = t * 4;
-    const int img0 = (int)(((long long)blockIdx.x * blockDim.x * 4) / A);
-    float v[4];
-    int n = 0;
-    if (e0 < total) {
-        n = 4;
-        if (vec_ok && e0 + 4 <= total) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(a.cls) + t);
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    const long long blk0 = (long long)blockIdx.x * (256 * 4 * kCandVec);
+    const int img0 = (int)(blk0 / A);
+    float v[kCandVec][4];
+    long long e0[kCandVec];
+    int n[kCandVec];
+#pragma unroll
+    for (int u = 0; u < kCandVec; ++u) {                 // element blk0 + (u * 256 + tid) * 4: coalesced 16-byte loads
+        e0[u] = blk0 + ((long long)u * 256 + threadIdx.x) * 4;
+        n[u] = e0[u] < total ? (int)min(4LL, total - e0[u]) : 0;
+        if (vec_ok && n[u] == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(a.cls + e0[u]));
+            v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
         } else {
-            n = (int)min(4LL, total - e0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (j < n) ? __ldg(a.cls + e0 + j) : -__int_as_float(0x7f800000);
+            for (int j = 0; j < 4; ++j) v[u][j] = (j < n[u]) ? __ldg(a.cls + e0[u] + j) : -__int_as_float(0x7f800000);
         }
     }
-    unsigned long long key[4] = {0ULL, 0ULL, 0ULL, 0ULL};
-    int which[4] = {0, 0, 0, 0};
+    bool any = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j < n && v[j] > a.pre_thr) {
-            const long long e = e0 + j;
-            const int img = (int)(e / A);
-            key[j] = candidate_key(a, (int)(e - (long long)img * A), v[j]);
-            which[j] = img - img0;
+    for (int u = 0; u < kCandVec; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) any |= (j < n[u]) && (v[u][j] > a.pre_thr);
+    if (!__syncthreads_or(any)) return;                  // (also orders the zeroing of sm.cnt before the appends)
+    unsigned long long key[4 * kCandVec];
+    int which[4 * kCandVec];
+#pragma unroll
+    for (int u = 0; u < kCandVec; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            key[u * 4 + j] = 0ULL;
+            which[u * 4 + j] = 0;
+            if (j < n[u] && v[u][j] > a.pre_thr) {
+                const long long e = e0[u] + j;
+                const int img = (int)(e / A);
+                key[u * 4 + j] = candidate_key(a, (int)(e - (long long)img * A), v[u][j]);
+                which[u * 4 + j] = img - img0;
+            }
         }
-    }
-    __syncthreads();
-    append_candidates<4>(a, sm, img0, min(kCandImgs, a.B - img0), key, which);
+    append_candidates<4 * kCandVec>(a, sm, img0, min(kCandImgs, a.B - img0), key, which);
 }
 
 // Per-level NCHW logits [B, n_loc, gh, gw]: threads walk memory order, anchor index = off + (y*gw+x)*n_loc + k.
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(256) candidates_nchw_kernel(const AnchorTable 
             key[0] = candidate_key(a, t.off[l] + loc * t.n_loc + k, v);
         }
     }
-    __syncthreads();
+    if (!__syncthreads_or(key[0] != 0ULL)) return;       // (also orders the zeroing of sm.cnt before the appends)
     append_candidates<1>(a, sm, img, 1, key, which);
 }
 
@@ -494,10 +506,10 @@ int launch_detect(const AnchorTable &t, const DetectArgs &a, cudaStream_t s, cud
     int launches = 0;
     if (a.cls) {
         const long long total = (long long)a.B * t.num_anchors;
-        const long long threads = (total + 3) / 4;
+        const long long per_cta = 256LL * 4 * kCandVec;
         const int vec_ok = (reinterpret_cast<uintptr_t>(a.cls) % 16 == 0) ? 1 : 0;
         prof_mark(s, "candidates_flat");
-        candidates_flat_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, t.num_anchors, total, vec_ok);
+        candidates_flat_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 256, 0, s>>>(a, t.num_anchors, total, vec_ok);
     } else {
         dim3 grid((t.num_anchors + 255) / 256, a.B);
         prof_mark(s, "candidates_nchw");
