@@ -319,7 +319,11 @@ __device__ __forceinline__ int crop_count_persons(const PersonList &pl, int lane
 // in registers, the 16-person x 32-column item goes to the warp's staging box (dense rows, no swizzle) and a TMA reduce-add performs
 // x += y2 in L2 -- the same single fp32 rounding, no residual registers, 4 B / element less L2 -> SM traffic.
 // kCrop: the instantiation that can sample the crops itself (CropFuse); the others carry none of that code.
-template <bool kInPlace, bool kCrop>
+// kRed: fc1's K splits are added up by the L2 (red.global.add.f32 into ONE [persons, hidden] accumulator that the reduce
+// step reads, clears and converts) instead of being stored as 37 partial sums and read back -- no 12 MB read-back, but the
+// order of the additions, and with it the last bits of the logits, changes from run to run (MPN_PRN_RED_ADD=1; measured,
+// off by default: every bit-identity guarantee of the library rests on the fixed-order reduce).
+template <bool kInPlace, bool kCrop, bool kRed = false>
 __global__ void __launch_bounds__(kThreads, 1)
 prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_w2,
@@ -665,11 +669,14 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int m = item >= nb ? 1 : 0, ch = item - m * nb;
                     uint32_t r[16];
                     tmem_ld16(t_lane + (uint32_t)(m * kAccCols + ch * 16), r);
-                    float *dst = args.partial + (size_t)z * args.split_stride + (size_t)(ch * 16) * args.hidden + hq * kFc1N +
-                                 m * 128 + q * 32 + lane;
+                    float *dst = args.partial + (kRed ? (size_t)0 : (size_t)z * args.split_stride) +
+                                 (size_t)(ch * 16) * args.hidden + hq * kFc1N + m * 128 + q * 32 + lane;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (ch * 16 + j < N) __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
+                        if (ch * 16 + j < N) {
+                            if (kRed) atomicAdd(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));   // result unused: RED
+                            else __stcg(dst + (size_t)j * args.hidden, __uint_as_float(r[j]));
+                        }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -692,6 +699,25 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int total = N * vec_per_row;
                 const int per = (total + G - 1) / G;
                 const int v_end = min(total, (c + 1) * per);
+                if (kRed) {
+                    // the sums are complete in the accumulator: read, clear (for the next launch), bias, ReLU, bf16
+                    for (int v = c * per + tid_e; v < v_end; v += kEpiWarps * 32) {
+                        const int row = v / vec_per_row, c4 = v - row * vec_per_row;
+                        float4 *src = reinterpret_cast<float4 *>(args.partial + (size_t)row * args.hidden + col0 + c4 * 4);
+                        float4 tot = __ldcg(src);
+                        __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(args.b1 + col0 + c4 * 4));
+                        tot.x = fmaxf(__fadd_rn(tot.x, bb.x), 0.0f);
+                        tot.y = fmaxf(__fadd_rn(tot.y, bb.y), 0.0f);
+                        tot.z = fmaxf(__fadd_rn(tot.z, bb.z), 0.0f);
+                        tot.w = fmaxf(__fadd_rn(tot.w, bb.w), 0.0f);
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(tot.x, tot.y), hi = __floats2bfloat162_rn(tot.z, tot.w);
+                        uint2 o;
+                        o.x = *reinterpret_cast<const unsigned *>(&lo);
+                        o.y = *reinterpret_cast<const unsigned *>(&hi);
+                        __stcg(reinterpret_cast<uint2 *>(args.y1 + (size_t)row * args.hidden + col0 + c4 * 4), o);
+                    }
+                } else {
                 const int s_part = (args.splits + kRedThreads - 1) / kRedThreads;   // <= kRedLoads
                 const int grp = lane / kRedThreads, part = lane - kRedThreads * grp;
                 const int s_lo = part * s_part, s_hi = min(args.splits, s_lo + s_part);
@@ -733,6 +759,7 @@ prn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         o.y = *reinterpret_cast<const unsigned *>(&hi);
                         __stcg(reinterpret_cast<uint2 *>(args.y1 + (size_t)row * args.hidden + col0 + c4 * 4), o);
                     }
+                }
                 }
             }
             epi_bar_sync();
@@ -843,6 +870,8 @@ struct FusedState {
     unsigned long long *bar;   // grid barrier arrival counters, then the chunk counters of the fused crop ([splits, 4])
     unsigned long long *trace;
     int grid, splits, rows_cap;
+    bool red_add;              // MPN_PRN_RED_ADD=1: in-place launches add fc1's K splits up in L2 (kRed)
+    float *red_acc;            //   ... in this [rows_cap, hidden] accumulator: zero at creation, cleared by every reader
     const float *out_ptr;      // buffer maps.out describes (handle-owned buffers only)
 };
 
@@ -857,6 +886,7 @@ int prn_fused_prepare(mpn_handle *h)
     if (cudaFuncSetAttribute(prn_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(prn_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(prn_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(prn_fused_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prn_fused_kernel<true, true>, kThreads, kSmemBytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
@@ -871,9 +901,15 @@ int prn_fused_prepare(mpn_handle *h)
     if (st->splits > nkb1) st->splits = nkb1;
     if (st->splits > kRedThreads * kRedLoads) st->splits = kRedThreads * kRedLoads;   // partial loads one reduce thread keeps in flight
     st->rows_cap = h->prn_ws.n_max < kPrnFusedMaxRows ? h->prn_ws.n_max : kPrnFusedMaxRows;
+    {
+        const char *ra = getenv("MPN_PRN_RED_ADD");
+        st->red_add = ra && ra[0] == '1' && kWaves == 1;
+    }
     st->split_stride = (size_t)st->rows_cap * Hd;
     const uint64_t rows = (uint64_t)h->prn_ws.n_max;
     bool ok = cudaMalloc(&st->partial, (size_t)st->splits * st->split_stride * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&st->red_acc, st->split_stride * sizeof(float)) == cudaSuccess &&
+              cudaMemset(st->red_acc, 0, st->split_stride * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&st->bar, (2 * kWaves * kBarLine + 4 * st->splits) * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(st->bar, 0, (2 * kWaves * kBarLine + 4 * st->splits) * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && encode_2d(&st->maps.x, h->crops_bf16, rows, (uint64_t)D, kXBox) &&
@@ -883,6 +919,7 @@ int prn_fused_prepare(mpn_handle *h)
     if (!ok) {
         cudaGetLastError();
         if (st->partial) cudaFree(st->partial);
+        if (st->red_acc) cudaFree(st->red_acc);
         if (st->bar) cudaFree(st->bar);
         delete st;
         snprintf(h->err, sizeof(h->err), "fused PRN setup failed (allocation or cuTensorMapEncodeTiled)");
@@ -897,6 +934,7 @@ void prn_fused_release(mpn_handle *h)
     FusedState *st = static_cast<FusedState *>(h->fused);
     if (!st) return;
     cudaFree(st->partial);
+    cudaFree(st->red_acc);
     cudaFree(st->bar);
     if (st->trace) cudaFree(st->trace);
     delete st;
@@ -970,6 +1008,7 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     const bool in_place = x_f32 == logits;
+    if (in_place && st->red_add && !fc) a.partial = st->red_acc;
     if (in_place && st->out_ptr != logits) {
         const uint64_t rows = n_dev ? (uint64_t)h->prn_ws.n_max : (uint64_t)n_host;    // mpn_prn: the caller's buffer has n_host rows
         if (!encode_2d_f32_box(&st->maps.out, logits, rows, (uint64_t)h->D, 32, kXBox) ||
@@ -979,6 +1018,9 @@ int launch_prn_fused(mpn_handle *h, const float *x_f32, const int *n_dev, int n_
     }
     cudaError_t e = fc ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true, true>, st->maps.x, st->maps.w1, st->maps.y1, st->maps.w2,
                                             st->maps.out, st->maps.out16, a)
+                  : (in_place && st->red_add)
+                      ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true, false, true>, st->maps.x, st->maps.w1, st->maps.y1,
+                                           st->maps.w2, st->maps.out, st->maps.out16, a)
                   : in_place ? cudaLaunchKernelEx(&cfg, prn_fused_kernel<true, false>, st->maps.x, st->maps.w1, st->maps.y1,
                                                   st->maps.w2, st->maps.out, st->maps.out16, a)
                              : cudaLaunchKernelEx(&cfg, prn_fused_kernel<false, false>, st->maps.x, st->maps.w1, st->maps.y1,

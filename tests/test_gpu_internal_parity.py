@@ -391,3 +391,38 @@ def test_fused_crop_equals_the_crop_kernel_bit_for_bit(weights, monkeypatch, key
             assert np.array_equal(gb, ga), k
     if a["launches"] is not None:
         assert b["launches"] == a["launches"] - 1, (a["launches"], b["launches"])      # no crop kernel
+
+
+def test_prn_red_add_variant_matches_the_fixed_order_reduce(weights, monkeypatch):
+    """MPN_PRN_RED_ADD=1 (measured variant, off by default): the K splits of fc1 are added up by the L2 instead of being
+    stored and reduced in a fixed order.  Same logits up to the order of 37 fp32 additions (detector/prn.py:20), call after
+    call (every reader clears the accumulator), and keypoints that are legitimate maxima of the default path's logits."""
+    wl = synthetic.WORKLOADS["c2"]
+    inp = synthetic.make_inputs(wl, batch=4)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MPN_PRN_RED_ADD", flag)
+        det = make_det(weights, wl, 4, prn_mode="bf16", prn_modes_allocated=("bf16",))
+        try:
+            dev_in = [_cuda(inp[k]) for k in ("encoded_boxes", "class_logits", "heatmap_logits")]
+            got = []
+            for rep in range(3):
+                out = det.run_device(*dev_in)
+                torch.cuda.synchronize()
+                N = int(out["person_offsets"].cpu().numpy()[-1])
+                got.append((det.debug_fetch("logits").reshape(-1, 56 * 36 * 17)[:N].cpu().numpy().copy(),
+                            out["keypoint_positions"].cpu().numpy()[:N].copy()))
+            outs.append(got)
+        finally:
+            det.close()
+    ref_logits, ref_pos = outs[0][0]
+    scale = np.abs(ref_logits).max()
+    for rep, (lg, pos) in enumerate(outs[1]):
+        assert lg.shape == ref_logits.shape
+        err = np.abs(lg - ref_logits).max() / scale
+        # (a different order of 37 fp32 additions flips the bf16 rounding of a few y1 values: RTOL_BF16_EMUL's effect)
+        assert err < RTOL_BF16_EMUL, f"call {rep}: logits differ by {err:.2e} of the scale"
+        flat = ref_logits.reshape(len(lg), 2016, 17)
+        yx = np.rint(pos * np.array([56, 36], np.float32)).astype(np.int64)
+        at = np.take_along_axis(flat, (yx[..., 0] * 36 + yx[..., 1])[:, None, :], 1)[:, 0]
+        assert ((flat.max(1) - at) / scale).max() < 2 * RTOL_BF16_EMUL
