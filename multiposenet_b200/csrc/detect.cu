@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
     // with one barrier per kept box -- among 4 warps that costs a third of what it costs among 32 -- while the long tail
     // mostly dies in the parallel test against the boxes kept so far.
     int step = C <= kChunk ? kChunk : 128;
+    int n_chunk = 0;
     for (int base = 0, n = 0; base < C && kept < a.max_det; base += n, step = min(2 * step, kChunk)) {
         n = min(step, C - base);
         // ---- a, b: decode, test against the boxes kept so far
@@ -413,10 +414,39 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
             sm.box[tid] = box;
             nb = nms_prepare(box);
             sm.nbox[tid] = nb;
-            for (int j = 0; j < kept; ++j)
-                if (nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr) { alive = false; break; }
+        }
+        // A survivor has to be tested against EVERY kept box: one thread walking ~88 boxes of a crowded image is 10-18 us
+        // per chunk (profiles/r03d_nms_chunks.txt), whatever the chunk's size.  While a chunk has fewer candidates than the
+        // CTA has threads, g threads share a candidate's walk (kept boxes p, p + g, ...; combined by shuffles); a full
+        // chunk takes four kept boxes per trip, their overlaps computed independently of each other.
+        const int share = kept > 0 ? kNmsThreads / n : 1;
+        if (share >= 2) {
+            int g = 2;
+            while (g * 2 <= share && g < 32) g *= 2;
+            __syncthreads();                           // sm.nbox of the chunk complete
+            const int cnd = tid / g, p = tid & (g - 1);
+            bool hit = false;
+            if (cnd < n) {
+                const NmsBox cb = sm.nbox[cnd];
+                for (int j = p; j < kept; j += g)
+                    if (nms_iou(cb, sm.kept_nbox[j]) > a.iou_thr) { hit = true; break; }
+            }
+            for (int o = g >> 1; o > 0; o >>= 1) hit |= __shfl_xor_sync(0xffffffffu, hit ? 1 : 0, o) != 0;
+            if (cnd < n && p == 0) sm.kept_local[cnd] = hit ? 0 : 1;
+            __syncthreads();
+            if (tid < n) alive = sm.kept_local[tid] != 0;
+        } else if (alive) {
+            int j = 0;
+            for (; j + 4 <= kept; j += 4) {
+                const bool o0 = nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr, o1 = nms_iou(nb, sm.kept_nbox[j + 1]) > a.iou_thr;
+                const bool o2 = nms_iou(nb, sm.kept_nbox[j + 2]) > a.iou_thr, o3 = nms_iou(nb, sm.kept_nbox[j + 3]) > a.iou_thr;
+                if (o0 | o1 | o2 | o3) { alive = false; break; }
+            }
+            for (; alive && j < kept; ++j)
+                if (nms_iou(nb, sm.kept_nbox[j]) > a.iou_thr) alive = false;
         }
         if (base == 0) nms_stamp(a, 3);                // first chunk decoded and tested against the kept boxes
+        if (n_chunk < 5) nms_stamp(a, 6 + 2 * n_chunk); // chunk i: tested against the kept boxes (slot 6 + 2 i) ...
         const int n_warps = (n + 31) >> 5;             // warps that hold candidates of this chunk
         if (warp >= n_warps && lane == 0) { sm.alive[0][warp] = 0u; sm.alive[1][warp] = 0u; }
         __syncthreads();                               // sm.box complete, idle warps' ballots zeroed
@@ -461,6 +491,8 @@ __global__ void __launch_bounds__(T, 1) sort_nms_kernel(const AnchorTable t, con
         }
         kept += nk;
         __syncthreads();
+        if (n_chunk < 5) nms_stamp(a, 7 + 2 * n_chunk); // ... and resolved (slot 7 + 2 i)
+        ++n_chunk;
     }
     nms_stamp(a, 4);                                   // all chunks resolved
     // zero padding (detector/utils/nms.py:47-52)

@@ -12,8 +12,8 @@ det = Detector(None, DetectorConfig(max_batch=wl.batch, max_height=wl.height, ma
 inp = synthetic.make_inputs(wl)
 enc, cls = torch.from_numpy(inp["encoded_boxes"]).cuda(), torch.from_numpy(inp["class_logits"]).cuda()
 det.nms_trace(True)
-names = ["CTA resident", "candidates complete", "keys sorted", "first chunk decoded", "all chunks resolved", "results published",
-         "person list built"]
+names = ["CTA resident", "candidates complete", "keys sorted", "first chunk decoded", "all chunks resolved", "results published"] + \
+        [f"chunk {i // 2} {'tested vs kept' if i % 2 == 0 else 'resolved'}" for i in range(10)]
 for rep in range(3):
     for _ in range(20):
         out = det.detect(enc, cls, (wl.height, wl.width))
