@@ -291,7 +291,8 @@ def _full_run_case(weights, key, batch, mode, sample):
 
 @pytest.mark.parametrize("key,batch,mode,sample", [
     ("tiny", None, "bf16", 64), ("tiny", None, "fp32", 64), ("c1", None, "bf16", 64), ("c1", None, "fp32", 16),
-    ("c2", 8, "bf16", 64), ("c2", 8, "fp32", 24), ("c3", 32, "bf16", 64), ("c4", 64, "bf16", 64)])
+    ("c2", 8, "bf16", 64), ("c2", 8, "fp32", 24), ("c3", 32, "bf16", 64), ("c4", 64, "bf16", 64),
+    ("c3", 1, "fp32", 24), ("c3", 2, "fp32", 24)])   # fp32 mode with 2 and 3 person groups of the tensor-core PRN
 def test_full_run_internal_buffers_and_sampled_rows(weights, key, batch, mode, sample):
     """BASELINE configs[0..3] at their full batch sizes (c4 on ONE GPU takes the per-tap crop path)."""
     _full_run_case(weights, key, batch, mode, sample)
