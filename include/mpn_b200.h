@@ -247,7 +247,9 @@ MPN_API int mpn_set_profiling(mpn_handle *h, int32_t enable);
 MPN_API int mpn_get_profile(mpn_handle *h, int32_t capacity, const char **names, float *ms, int32_t *count);
 
 /* Development aid for timing experiments: stages whose bit is set are NOT launched by mpn_run (their outputs keep the
- * values of the previous call): 1 detect, 2 heatmap stage, 8 crop, 16 PRN, 32 keypoint decode.  0 = normal. */
+ * values of the previous call): 1 detect, 2 heatmap stage, 8 crop, 16 PRN, 32 keypoint decode.  64 (only with
+ * MPN_FUSE_CROP=1, the crop inside the single-kernel PRN): that kernel samples the crops and stops, so that they can be
+ * fetched.  0 = normal. */
 MPN_API int mpn_debug_skip(mpn_handle *h, uint32_t mask);
 
 /* Development aid: globaltimer stamps (ns) of the phases of the most recent single-kernel PRN launch, 16 slots per CTA:
